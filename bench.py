@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py — CEM-MPC plans/sec + ensemble transitions/sec at the PointGoal1 shape (BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA planner
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU planner (oracle port)
+
+A "step" is ONE planning call (policy.generate_action: 5 CEM iterations of sample -> fused ensemble
+rollout + scoring -> score-reduce -> select -> refit) at BASELINE configs[1] (C1 dims: 5-member
+4x128 ensemble, obs 60, act 2, horizon 15, population 150, 20 particles, 5 iterations, all of
+which run: stddev_threshold = 0).
+  value  = plans/sec with the state already in HBM, timed with CUDA events around each plan, L2
+           flushed between plans, max over ranks.
+  e2e    = plans/sec through policy.generate_action(numpy_state): host buffers in, host buffers
+           out, H2D + D2H + synchronisation inside the timed region.
+N > 1: one process per GPU (torchrun); every rank plans its own independent states (weak scaling,
+no data-path collective — batched planning of BASELINE configs[3]); value = all ranks' plans / max
+time. `--extras c3` adds the population-65536 plan sharded over the ranks with the per-iteration
+NCCL all-gather (strong scaling) as extra keys.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, 'ethz-safe-learning_b200')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "CEM-MPC plans/sec (PointGoal1 shape; ensemble transitions/sec alongside)"
+UNIT = "plans/s"
+
+
+def workload_config(c, precision, extra=None):
+    cfg = {"workload": "BASELINE configs[1] (C1 dims): E=%d L=%dx%d O=%d A=%d H=%d N=%d P=%d I=%d K=%d, "
+                       "SafeCemMpc penalty objective, stddev_threshold=0 (all iterations run)"
+                       % (c['E'], c['L'], c['U'], c['O'], c['A'], c['H'], c['N'], c['P'], c['I'], c['K']),
+           "rollout_precision": precision, "l2": "flushed between timed plans (256 MiB write)",
+           "rng": "Philox4x32-10 on device"}
+    cfg.update(extra or {})
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.check_output(
+                    ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                     "--format=csv,noheader,nounits"], timeout=5).decode().strip()
+                self.rows.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4)
+                          if r[2 + i].lower().startswith('active')})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU planner (the oracle port) — cpu_baseline leg and --impl reference
+# ------------------------------------------------------------------------------------------------
+def time_cpu_planner(c, budget_s=20.0, max_plans=12):
+    """Times the numpy restatement of the reference planner (oracle/simba_oracle.py) on this box's
+    host cores: whole C1 plans with Philox-contract normals pre-generated outside the timed region."""
+    from oracle import simba_oracle as so           # the only product-side use: the CPU baseline
+    from tests import helpers
+    from simba_b200 import synthetic
+    z, eps, zf = synthetic.make_draws(c['I'], 1, c['N'], c['H'], c['A'], c['P'], c['O'], seed=2)
+    pl = helpers.oracle_planner(c, 'penalty')
+    pl.do_generate_action(c['state'], z[:, 0], eps[:, 0], zf[0])          # warm-up (BLAS threads, pages)
+    times, t_start = [], time.perf_counter()
+    while len(times) < max_plans and (time.perf_counter() - t_start < budget_s or len(times) < 2):
+        t0 = time.perf_counter()
+        _, _, n = pl.do_generate_action(c['state'], z[:, 0], eps[:, 0], zf[0])
+        times.append(time.perf_counter() - t0)
+    best, med = min(times), float(np.median(times))
+    try:
+        import threadpoolctl
+        threads = max([p.get('num_threads', 1) for p in threadpoolctl.threadpool_info()] or [1])
+    except Exception:
+        threads = os.cpu_count()
+    return {"value": 1.0 / med, "unit": UNIT, "cores": int(threads), "kind": "port",
+            "sample": "%d whole C1 plans (numpy fp32 restatement of the TensorFlow reference, "
+                      "BLAS threads=%d of %d host cpus); median %.1f ms, best %.1f ms per plan"
+                      % (len(times), threads, os.cpu_count(), med * 1e3, best * 1e3),
+            "transitions_per_s": n * c['H'] * c['P'] * c['N'] / med, "ms_per_plan_median": med * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from simba_b200 import synthetic
+    c = synthetic.make_workload('c1')
+    cb = time_cpu_planner(c, budget_s=15.0 * max(1, args.steps) / 5.0, max_plans=max(2, args.steps + args.warmup))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_plan_median"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (random-init ensemble, synthetic state; reference TensorFlow planner is not "
+                    "installable here, so this is the oracle port on host cores)",
+            "config": workload_config(c, "f32 (CPU)"), "cpu_baseline": cb, "gpu_launches": 0,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "transitions_per_s": cb["transitions_per_s"]}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--extras', default='', help="comma list of: c3, c4, fp32")
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from simba_b200 import _lib, synthetic
+    import ctypes as C
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU planner)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    lib = _lib.load()
+    W, K = max(3, args.warmup), max(1, args.steps)
+
+    c = synthetic.make_workload('c1')
+    precision = args.precision
+    pol = synthetic.build_policy(c, 'penalty', precision=precision, seed=0x5EED + 1000 * rank)
+    try:
+        pol.build()
+    except _lib.SimbaError as e:
+        if e.code != -6:
+            raise
+        precision = 'fp32'
+        pol = synthetic.build_policy(c, 'penalty', precision=precision, seed=0x5EED + 1000 * rank)
+        pol.build()
+    n_pool = 16
+    states_np = synthetic.make_state(c['sensors'], seed=100 + rank, n_states=n_pool)
+    states = torch.from_numpy(states_np).cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    out_a = torch.empty((1, c['A']), dtype=torch.float32, device='cuda')
+    out_s = torch.empty((1,), dtype=torch.float32, device='cuda')
+    out_i = torch.empty((1,), dtype=torch.int32, device='cuda')
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput --------------------------------------------------------------
+    for k in range(W):
+        pol.plan_device(states[k % n_pool:k % n_pool + 1], None, out_a, out_s, out_i)
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    iters_total = 0
+    sync_all()
+    t_wall0 = time.perf_counter()
+    for k in range(K):
+        flush.fill_(k & 0xff)
+        ev[k][0].record()
+        pol.plan_device(states[k % n_pool:k % n_pool + 1], None, out_a, out_s, out_i)
+        ev[k][1].record()
+    sync_all()
+    t_wall = time.perf_counter() - t_wall0
+    ms = np.array([a.elapsed_time(b) for a, b in ev])
+    iters_total = int(out_i.cpu()[0])
+    t_rank = torch.tensor([ms.sum() / 1e3], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t_rank, op=dist.ReduceOp.MAX)
+    t_dev = float(t_rank.cpu()[0])
+    value = world * K / t_dev
+    launches = pol.launches_per_plan * K
+
+    # ---- end to end through the public API (host buffers) ----------------------------------------
+    for k in range(W):
+        pol.generate_action(states_np[k % n_pool])
+    sync_all()
+    t_e2e = 0.0
+    for k in range(K):
+        flush.fill_(k & 0xff)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        a = pol.generate_action(states_np[k % n_pool])
+        t_e2e += time.perf_counter() - t0
+    assert np.all(np.isfinite(a))
+    t_e = torch.tensor([t_e2e], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * K / float(t_e.cpu()[0])
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the dominant kernel alone: fused rollout, CUDA events on the launching stream -------------
+    planner = pol._ensure_planner()
+    B = c['P'] * c['N']
+    acts = torch.empty((1, c['N'], c['H'], c['A']), dtype=torch.float32, device='cuda').uniform_(-1, 1)
+    r_ret = torch.empty(B, dtype=torch.float32, device='cuda')
+    r_msk = torch.empty(B, dtype=torch.int64, device='cuda')
+    r_sum = torch.empty(B, dtype=torch.float32, device='cuda')
+    st_ptr = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def rollout_once(it):
+        _lib.check(lib.simba_rollout_score(planner, C.c_void_p(states.data_ptr()), C.c_void_p(acts.data_ptr()),
+                                           None, 0x5EED, it, None, C.c_void_p(r_ret.data_ptr()),
+                                           C.c_void_p(r_msk.data_ptr()), C.c_void_p(r_sum.data_ptr()), st_ptr))
+    for it in range(5):
+        rollout_once(it)
+    torch.cuda.synchronize()
+    n_roll = min(200, max(20, K))
+    rev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_roll)]
+    for k in range(n_roll):
+        flush.fill_(k & 0xff)
+        rev[k][0].record()
+        rollout_once(k % c['I'])
+        rev[k][1].record()
+    torch.cuda.synchronize()
+    roll_ms = float(np.mean([a.elapsed_time(b) for a, b in rev]))
+    fpt = synthetic.flops_per_transition(c['O'], c['A'], c['L'], c['U'])
+    flops_per_launch = fpt * c['H'] * B
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak_tf = peaks.get('bf16_tflops', 1590.0)
+    achieved_tf = flops_per_launch / (roll_ms * 1e-3) / 1e12
+    ms_plan = ms.mean()
+    roofline = {"kernel": "rollout_tc_kernel" if precision == 'bf16' else "rollout_f32_kernel",
+                "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PFLOP/s",
+                "flops_per_launch": flops_per_launch, "launch_ms": roll_ms,
+                "share_of_plan": c['I'] * roll_ms / ms_plan,
+                "note": "C1 is latency-bound: %d row tiles on 148 SMs, %d dependent GEMM stages per launch"
+                        % ((B + 127) // 128 if precision == 'bf16' else (B + 31) // 32, c['H'] * (c['L'] + 1))}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": float(ms_plan), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if precision == 'bf16' else "f32", "data": "synthetic (random-init ensemble, synthetic states)",
+            "config": workload_config(c, "bf16 tcgen05, fp32 accumulate" if precision == 'bf16' else "fp32 SIMT",
+                                      {"parallelism": "independent plans per GPU (no collective)" if world > 1 else "1 GPU"}),
+            "transitions_per_s": world * K * iters_total * c['H'] * B / t_dev,
+            "iterations_run_per_plan": iters_total,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": c['O'] * 4 + 8,
+                    "d2h_bytes_per_step": c['A'] * 4 + 8},
+            "gpu_launches": launches, "launches_per_plan": pol.launches_per_plan,
+            "clocks": clocks, "roofline": roofline, "wall_s_timed_loop": t_wall}
+
+    # ---- extras -----------------------------------------------------------------------------------
+    extras = {}
+    want = [x for x in args.extras.split(',') if x]
+    if 'fp32' in want and precision != 'fp32':
+        extras['fp32'] = bench_plain(synthetic, torch, c, 'fp32', states, flush, min(K, 50))
+    if 'c4' in want:
+        extras['c4'] = bench_batched(synthetic, torch, precision, flush, world, rank)
+    if 'c3' in want:
+        extras['c3'] = bench_c3(synthetic, torch, dist, lib, _lib, precision, world, rank)
+    if extras:
+        line['extras'] = extras
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'] = time_cpu_planner(c)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_plain(synthetic, torch, c, precision, states, flush, K):
+    pol = synthetic.build_policy(c, 'penalty', precision=precision, seed=7)
+    for k in range(3):
+        pol.plan_device(states[k:k + 1])
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for k in range(K):
+        flush.fill_(k & 0xff)
+        ev[k][0].record()
+        pol.plan_device(states[k % 16:k % 16 + 1])
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    return {"plans_per_s": 1e3 / ms, "ms_per_plan": ms, "precision": precision}
+
+
+def bench_batched(synthetic, torch, precision, flush, world, rank, S=1024):
+    """BASELINE configs[3]: S independent states per call (sharded over ranks, no collective)."""
+    S_local = S // world
+    c = synthetic.make_workload('c1', S=S_local, seed=0)
+    pol = synthetic.build_policy(c, 'penalty', precision=precision, seed=11 + rank)
+    st = torch.from_numpy(synthetic.make_state(c['sensors'], seed=300 + rank, n_states=S_local)).cuda()
+    for _ in range(2):
+        pol.plan_device(st)
+    torch.cuda.synchronize()
+    K = 5
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for k in range(K):
+        flush.fill_(k & 0xff)
+        ev[k][0].record()
+        pol.plan_device(st)
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    fpt = synthetic.flops_per_transition(c['O'], c['A'], c['L'], c['U'])
+    trans = c['I'] * c['H'] * c['P'] * c['N'] * S_local
+    return {"states_per_call_per_gpu": S_local, "ms_per_call": ms, "plans_per_s_per_gpu": S_local * 1e3 / ms,
+            "transitions_per_s_per_gpu": trans / (ms * 1e-3), "tflops_per_gpu": trans * fpt / (ms * 1e-3) / 1e12}
+
+
+def bench_c3(synthetic, torch, dist, lib, _lib, precision, world, rank):
+    """BASELINE configs[2]: population 65536, 32 particles, horizon 30, sharded over the ranks with one
+    NCCL all-gather of (return, cost) per iteration. E=5 does not divide P=32 (the reference's tf.split
+    would raise) -> member_map='particle'."""
+    import ctypes as C
+    c = synthetic.make_workload('c3')
+    pol = synthetic.build_policy(c, 'penalty', precision=precision, member_map='particle', seed=21,
+                                 rank=rank, world_size=world)
+    pol.build()
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_char * 128)()
+            _lib.check(lib.simba_nccl_unique_id(buf))
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        pol.init_distributed(bytes(uid.cpu().numpy().tobytes()))
+    st = torch.from_numpy(synthetic.make_state(c['sensors'], seed=400, n_states=1).reshape(1, -1)).cuda()
+    pol.plan_device(st, seed=5)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    K = 2
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    outs = []
+    for k in range(K):
+        ev[k][0].record()
+        outs.append(pol.plan_device(st, seed=5 + k)[0].clone())
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    t = torch.tensor([np.mean([a.elapsed_time(b) for a, b in ev])], dtype=torch.float64, device='cuda')
+    same = torch.ones(1, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ref = outs[-1].clone()
+        dist.broadcast(ref, 0)
+        same = (ref == outs[-1]).all().float().reshape(1)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    ms = float(t.cpu()[0])
+    fpt = synthetic.flops_per_transition(c['O'], c['A'], c['L'], c['U'])
+    trans = c['I'] * c['H'] * c['P'] * c['N']
+    return {"ms_per_plan": ms, "plans_per_s": 1e3 / ms, "transitions_per_s": trans / (ms * 1e-3),
+            "tflops_total": trans * fpt / (ms * 1e-3) / 1e12, "replicas_bit_identical": bool(same.cpu()[0] > 0),
+            "member_map": "particle", "scaling": "strong"}
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,547 @@
+// The small CEM kernels around the rollout: action sampling, cross-particle score reduction,
+// elite selection (radix select), moment refit, final noise — plus the batch versions of the
+// reference's public scorer / scale / compute_objective methods. All are HBM / latency bound:
+// coalesced, vectorised where the layout allows, no tensor cores.
+#include "cem_kernels.cuh"
+
+namespace simba {
+
+// =============================================================================================
+// k1  action sampling — simba/policies/cem_mpc.py:44-48
+//     a = clip_by_value(z * sigma + mu, lb, ub);  z external or Philox stream ACTION.
+// One thread = 4 consecutive flattened (h, a) elements of one candidate (= one Philox block).
+// =============================================================================================
+__global__ void __launch_bounds__(256) sample_actions_kernel(SampleParams p) {
+  const int HA = p.H * p.A;
+  const int JB = (HA + 3) >> 2;
+  const long total = (long)p.S * p.N * JB;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % JB);
+    const long si = idx / JB;                 // s * N + i
+    const int s = (int)(si / p.N);
+    const int i = (int)(si - (long)s * p.N);
+    if (p.active != nullptr && p.active[s] == 0) continue;
+    const long base = si * HA + 4 * j;
+    float z[4];
+    if (p.z != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) z[q] = (4 * j + q < HA) ? p.z[base + q] : 0.0f;
+    } else {
+      const float4 n = philox_normals<false>(p.seed_ptr ? *p.seed_ptr : p.seed, kStreamAction, (uint32_t)s,
+                                             (uint32_t)p.iteration, 0u, (uint32_t)i, (uint32_t)j);
+      z[0] = n.x; z[1] = n.y; z[2] = n.z; z[3] = n.w;
+    }
+    float out[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = 4 * j + q;
+      if (e < HA) {
+        const int a = e % p.A;
+        const float v = __fadd_rn(__fmul_rn(z[q], p.sigma[s * HA + e]), p.mu[s * HA + e]);
+        out[q] = fminf(fmaxf(v, p.lb[a]), p.ub[a]);
+      }
+    }
+    if ((HA & 3) == 0) {
+      *reinterpret_cast<float4*>(p.out + base) = make_float4(out[0], out[1], out[2], out[3]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (4 * j + q < HA) p.out[base + q] = out[q];
+    }
+  }
+}
+
+cudaError_t launch_sample_actions(const SampleParams& p, cudaStream_t st) {
+  const int HA = p.H * p.A;
+  const long total = (long)p.S * p.N * ((HA + 3) / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  sample_actions_kernel<<<blocks, 256, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// k8  cross-particle reduction — simba/policies/mpc_policy.py:38-39,
+//     simba/policies/safe_cem_mpc.py:94-96 (mean return), :110-120 (per-step particle counts of
+//     the done-masked cost -> Beta posterior test), :98-108 (mean cost sum).
+// One thread per (state, local candidate); loads are coalesced across candidates for each
+// particle. Per-step counts use bit-sliced (carry-save) counters over the 64-bit cost masks, so
+// the H x P popcount costs ~3 logic ops per particle and plane. Summation order over particles
+// is fixed (p ascending) => bit-identical on every rank.
+// =============================================================================================
+__global__ void __launch_bounds__(256) score_reduce_kernel(ReduceParams p) {
+  const long total = (long)p.S * p.N_local;
+  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int s = (int)(idx / p.N_local);
+  const int i = (int)(idx - (long)s * p.N_local);
+  if (p.active != nullptr && p.active[s] == 0) return;
+  float ret = 0.0f, csum = 0.0f;
+  uint64_t plane[8];
+#pragma unroll
+  for (int b = 0; b < 8; ++b) plane[b] = 0ull;
+  for (int q = 0; q < p.P; ++q) {
+    const long r = ((long)s * p.P + q) * p.N_local + i;
+    ret = __fadd_rn(ret, p.row_return[r]);
+    csum = __fadd_rn(csum, p.row_costsum[r]);
+    uint64_t carry = p.row_costmask[r];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const uint64_t t = plane[b] & carry;
+      plane[b] ^= carry;
+      carry = t;
+    }
+  }
+  const float mean_ret = __fdiv_rn(ret, (float)p.P);
+  float cost = 0.0f;
+  if (p.objective == SIMBA_OBJ_LEAST_COST) {
+    cost = __fdiv_rn(csum, (float)p.P);
+  } else if (p.objective != SIMBA_OBJ_REWARD) {
+    uint64_t cand = (p.H >= 64) ? ~0ull : ((1ull << p.H) - 1ull);
+    int maxc = 0;
+#pragma unroll
+    for (int b = 7; b >= 0; --b) {
+      const uint64_t m = cand & plane[b];
+      if (m) { cand = m; maxc |= (1 << b); }
+    }
+    cost = (float)maxc;
+  }
+  reinterpret_cast<float2*>(p.out_pairs)[idx] = make_float2(mean_ret, cost);
+}
+
+cudaError_t launch_score_reduce(const ReduceParams& p, cudaStream_t st) {
+  const long total = (long)p.S * p.N_local;
+  score_reduce_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// k9  elite selection — simba/policies/cem_mpc.py:56-60
+//     top_k(scores, K, sorted=False) with ties -> lower index; argmax; strict '>' best-so-far.
+// One CTA per state. Candidates get a 64-bit order key (larger = better); an MSD radix select
+// (8-bit digits, shared-memory histogram) finds the K-th largest key; one ordered compaction
+// (two block scans) emits the elite set in ascending index order, which makes the refit's
+// summation order — and therefore mu/sigma — bit-identical on every rank.
+// =============================================================================================
+__device__ __forceinline__ uint32_t ordered_u32(float f) {
+  f = f + 0.0f;                                   // -0 -> +0 so that -0 == +0 ties by index
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ float pair_score(int objective, float ret, float cost, float c_max) {
+  switch (objective) {
+    case SIMBA_OBJ_REWARD: return ret;
+    case SIMBA_OBJ_LEAST_COST: return -cost;
+    default:   // SAFE_PENALTY (safe_cem_mpc.py:96) and the score FEASIBLE_FIRST reports
+      return __fsub_rn(ret, __fmul_rn(cost > c_max ? 1.0f : 0.0f, 100.0f));
+  }
+}
+
+__device__ __forceinline__ uint64_t pair_key(int objective, float ret, float cost, float c_max) {
+  if (objective == SIMBA_OBJ_FEASIBLE_FIRST) {
+    if (cost <= c_max) return (1ull << 63) | (uint64_t)ordered_u32(ret);
+    const uint32_t viol = (uint32_t)fminf(cost, 255.0f);
+    return ((uint64_t)(255u - viol) << 32) | (uint64_t)ordered_u32(ret);
+  }
+  return (uint64_t)ordered_u32(pair_score(objective, ret, cost, c_max));
+}
+
+template <int NT>
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += n;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = (lane < NT / 32) ? warp_sums[lane] : 0;
+    int wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += n;
+    }
+    if (lane < NT / 32) warp_sums[lane] = wi - w;     // exclusive warp offsets
+    if (lane == 31) *total = wi;
+  }
+  __syncthreads();
+  const int res = warp_sums[warp] + incl - v;
+  __syncthreads();
+  return res;
+}
+
+constexpr int kSelectThreads = 1024;
+
+__global__ void __launch_bounds__(kSelectThreads) select_elites_kernel(SelectParams p) {
+  const int s = blockIdx.x;
+  if (p.active != nullptr && p.active[s] == 0) return;
+  __shared__ int hist[256];
+  __shared__ int warp_sums[32];
+  __shared__ int sh_total;
+  __shared__ int sh_digit, sh_need;
+  __shared__ unsigned long long sh_best_key;
+  __shared__ int sh_best_idx;
+  const int tid = threadIdx.x;
+  const int N = p.N, K = p.K;
+  // candidate i lives at pairs_all[(g * S + s) * N_local + (i % N_local)], g = i / N_local
+  auto load_pair = [&](int i) {
+    const int gsh = i / p.N_local, il = i - gsh * p.N_local;
+    return reinterpret_cast<const float2*>(p.pairs_all)[((long)gsh * p.S + s) * p.N_local + il];
+  };
+  auto key_of = [&](int i) {
+    const float2 pr = load_pair(i);
+    return pair_key(p.objective, pr.x, pr.y, p.c_max);
+  };
+
+  // ---- MSD radix select of the K-th largest key ----------------------------------------------
+  uint64_t prefix = 0ull, mask = 0ull;
+  int need = K;
+  const int top_byte = (p.objective == SIMBA_OBJ_FEASIBLE_FIRST) ? 7 : 3;
+  if (tid == 0) { sh_best_key = 0ull; sh_best_idx = 0x7fffffff; }
+  for (int byte = top_byte; byte >= 0; --byte) {
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    const int shift = 8 * byte;
+    for (int i = tid; i < N; i += kSelectThreads) {
+      const uint64_t k = key_of(i);
+      if ((k & mask) == prefix) atomicAdd(&hist[(int)((k >> shift) & 0xffull)], 1);
+    }
+    __syncthreads();
+    if (tid < 256) {
+      int above = 0;
+      for (int b = tid + 1; b < 256; ++b) above += hist[b];
+      if (above < need && need <= above + hist[tid]) { sh_digit = tid; sh_need = need - above; }
+    }
+    __syncthreads();
+    prefix |= (uint64_t)sh_digit << shift;
+    mask |= 0xffull << shift;
+    need = sh_need;
+    __syncthreads();
+  }
+  const uint64_t T = prefix;   // K-th largest key; `need` of the keys == T are taken, lowest index first
+
+  // ---- ordered compaction: each thread owns a contiguous index range -------------------------
+  const int V = (N + kSelectThreads - 1) / kSelectThreads;
+  const int lo = min(N, tid * V), hi = min(N, lo + V);
+  int eq_local = 0;
+  uint64_t best_k = 0ull;
+  int best_i = 0x7fffffff;
+  for (int i = lo; i < hi; ++i) {
+    const uint64_t k = key_of(i);
+    eq_local += (k == T);
+    if (k > best_k || best_i == 0x7fffffff) { best_k = k; best_i = i; }   // first max in range
+  }
+  const int eq_before = block_exclusive_scan<kSelectThreads>(eq_local, warp_sums, &sh_total);
+  int sel_local = 0, eq_run = eq_before;
+  for (int i = lo; i < hi; ++i) {
+    const uint64_t k = key_of(i);
+    if (k > T) ++sel_local;
+    else if (k == T) { if (eq_run < need) ++sel_local; ++eq_run; }
+  }
+  int pos = block_exclusive_scan<kSelectThreads>(sel_local, warp_sums, &sh_total);
+  eq_run = eq_before;
+  for (int i = lo; i < hi; ++i) {
+    const uint64_t k = key_of(i);
+    bool sel = k > T;
+    if (k == T) { sel = eq_run < need; ++eq_run; }
+    if (sel) p.out_elite[(long)s * K + pos++] = i;
+    if (p.out_scores != nullptr) {
+      const float2 pr = load_pair(i);
+      p.out_scores[(long)s * N + i] = pair_score(p.objective, pr.x, pr.y, p.c_max);
+    }
+  }
+
+  // ---- best of elite = global best key, lowest index among ties (argmax first max) -----------
+  if (best_i != 0x7fffffff) atomicMax(&sh_best_key, (unsigned long long)best_k);
+  __syncthreads();
+  if (best_i != 0x7fffffff && best_k == sh_best_key) atomicMin(&sh_best_idx, best_i);
+  __syncthreads();
+  const int top = sh_best_idx;
+  const float2 pr = load_pair(top);
+  const float top_score = pair_score(p.objective, pr.x, pr.y, p.c_max);
+  if (top_score > p.best_score[s]) {                       // cem_mpc.py:58 strict '>'
+    if (tid < p.A) p.best_action[s * p.A + tid] = p.actions[((long)s * N + top) * p.H * p.A + tid];
+    __syncthreads();
+    if (tid == 0) p.best_score[s] = top_score;
+  }
+}
+
+cudaError_t launch_select_elites(const SelectParams& p, cudaStream_t st) {
+  select_elites_kernel<<<p.S, kSelectThreads, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// k10  refit — simba/policies/cem_mpc.py:61-67
+//      elites = gather(actions, elite); mean, var = moments(elites, axes=0) (population, two-pass);
+//      mu, sigma smoothing; early exit when mean(sigma) <= stddev_threshold.
+// One CTA per state; thread = (column c = (h, a), row group); partials are combined in a fixed
+// order (deterministic => bit-identical replicas).
+// =============================================================================================
+constexpr int kRefitThreads = 1024;
+
+__global__ void __launch_bounds__(kRefitThreads) refit_kernel(RefitParams p) {
+  const int s = blockIdx.x;
+  if (p.active != nullptr && p.active[s] == 0) return;
+  extern __shared__ float sh[];           // [groups][HA] partials, then [HA] mean, [HA] sigma
+  const int HA = p.H * p.A;
+  const int groups = kRefitThreads / HA > 0 ? kRefitThreads / HA : 1;
+  float* part = sh;
+  float* mean = part + groups * HA;
+  float* sig = mean + HA;
+  const int tid = threadIdx.x;
+  const int* elite = p.elite + (long)s * p.K;
+  const float* acts = p.actions + (long)s * p.N * HA;
+  const float kf = (float)p.K;
+
+  const int c = tid % HA, grp = tid / HA;                  // HA <= 1024 (checked at creation)
+  for (int pass = 0; pass < 2; ++pass) {
+    if (grp < groups) {
+      float acc = 0.0f;
+      const float m = pass ? mean[c] : 0.0f;
+      for (int k = grp; k < p.K; k += groups) {
+        const float v = acts[(long)elite[k] * HA + c];
+        if (pass) { const float d = __fsub_rn(v, m); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
+        else acc = __fadd_rn(acc, v);
+      }
+      part[grp * HA + c] = acc;
+    }
+    __syncthreads();
+    for (int cc = tid; cc < HA; cc += kRefitThreads) {
+      const int c = cc;
+      float tot = 0.0f;
+      for (int gI = 0; gI < groups; ++gI) tot = __fadd_rn(tot, part[gI * HA + c]);
+      const float r = __fdiv_rn(tot, kf);
+      if (pass == 0) mean[c] = r;
+      else {
+        const float sd = sqrtf(r);                                        // cem_mpc.py:63
+        const float mu_new = __fadd_rn(__fmul_rn(p.smoothing, p.mu[s * HA + c]),
+                                       __fmul_rn(p.one_minus_smoothing, mean[c]));
+        const float sg_new = __fadd_rn(__fmul_rn(p.smoothing, p.sigma[s * HA + c]),
+                                       __fmul_rn(p.one_minus_smoothing, sd));
+        p.mu[s * HA + c] = mu_new;                                        // cem_mpc.py:64-65
+        p.sigma[s * HA + c] = sg_new;
+        sig[c] = sg_new;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    float tot = 0.0f;
+    for (int c = 0; c < HA; ++c) tot = __fadd_rn(tot, sig[c]);
+    if (p.iterations_run != nullptr) p.iterations_run[s] += 1;
+    if (p.active != nullptr && __fdiv_rn(tot, (float)HA) <= p.stddev_threshold)  // cem_mpc.py:66-67
+      p.active[s] = 0;
+  }
+}
+
+cudaError_t launch_refit(const RefitParams& p, cudaStream_t st) {
+  const int HA = p.H * p.A;
+  const int groups = kRefitThreads / HA > 0 ? kRefitThreads / HA : 1;
+  const size_t smem = (size_t)(groups * HA + 2 * HA) * sizeof(float);
+  refit_kernel<<<p.S, kRefitThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// k11  final noise — simba/policies/cem_mpc.py:68 : best + z * noise_stddev (not re-clipped)
+// =============================================================================================
+__global__ void finalize_kernel(FinalizeParams p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.S * p.A) return;
+  const int s = idx / p.A, a = idx - s * p.A;
+  float z;
+  if (p.z != nullptr) z = p.z[idx];
+  else {
+    const float4 n = philox_normals<false>(p.seed_ptr ? *p.seed_ptr : p.seed, kStreamFinal, (uint32_t)s, 0u, 0u, 0u,
+                                           (uint32_t)(a >> 2));
+    const float zz[4] = {n.x, n.y, n.z, n.w};
+    z = zz[a & 3];
+  }
+  p.out[idx] = __fadd_rn(p.best[idx], __fadd_rn(__fmul_rn(z, p.noise_stddev), 0.0f));
+}
+
+cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t st) {
+  const int n = p.S * p.A;
+  finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+// plan bookkeeping: reset mu/sigma/best/active at the start of a plan (cem_mpc.py:36-42)
+__global__ void plan_init_kernel(PlanInitParams p) {
+  const int HA = p.H * p.A;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < p.S * HA) {
+    const int a = (idx % HA) % p.A;
+    p.mu[idx] = p.init_mean[a];
+    p.sigma[idx] = p.init_stddev[a];
+  }
+  if (idx < p.S * p.A) p.best_action[idx] = 0.0f;
+  if (idx < p.S) {
+    p.best_score[idx] = -INFINITY;
+    p.active[idx] = 1;
+    p.iterations_run[idx] = 0;
+  }
+}
+
+cudaError_t launch_plan_init(const PlanInitParams& p, cudaStream_t st) {
+  const int n = p.S * p.H * p.A;
+  plan_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+__global__ void plan_output_kernel(const float* best_score, const int32_t* iterations_run,
+                                   float* out_score, int32_t* out_iters, int S) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < S) {
+    out_score[idx] = best_score[idx];
+    if (out_iters != nullptr) out_iters[idx] = iterations_run[idx];
+  }
+}
+
+cudaError_t launch_plan_output(const float* best_score, const int32_t* iterations_run,
+                               float* out_score, int32_t* out_iters, int S, cudaStream_t st) {
+  plan_output_kernel<<<(S + 127) / 128, 128, 0, st>>>(best_score, iterations_run, out_score,
+                                                       out_iters, S);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// Batch versions of the reference's public helper methods
+// =============================================================================================
+// TransitionModel.scale — simba/models/transition_model.py:79-87
+__global__ void scale_kernel(const float* x, const float* smin, const float* sdelta, int scale_on,
+                             long total, int IN, float* out) {
+  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int k = (int)(idx % IN);
+  out[idx] = scale_on ? __fdiv_rn(__fsub_rn(x[idx], smin[k]), sdelta[k]) : x[idx];
+}
+
+cudaError_t launch_scale(const float* x, const float* smin, const float* sdelta, int scale_on,
+                         long batch, int IN, float* out, cudaStream_t st) {
+  const long total = batch * IN;
+  scale_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(x, smin, sdelta, scale_on, total, IN, out);
+  return cudaGetLastError();
+}
+
+// SafetyGymStateScorer.reward / .cost — simba/environment_utils/safety_gym.py:110-166
+__global__ void scorer_eval_kernel(simba_scorer_t sc, const float* obs, const float* next_obs,
+                                   int batch, int O, float* out_reward, int32_t* out_done,
+                                   float* out_cost) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= batch) return;
+  const float* a = obs + (long)r * O;
+  auto lda = [&](int b) { return a[b]; };
+  if (out_cost != nullptr) out_cost[r] = state_cost(sc, lda);
+  if (out_reward != nullptr && next_obs != nullptr) {
+    const float* n = next_obs + (long)r * O;
+    const float d0 = goal_distance(sc, lda);
+    const float d1 = goal_distance(sc, [&](int b) { return n[b]; });
+    const bool goal = d0 <= sc.goal_threshold;
+    out_reward[r] = step_reward(sc, d0, d1, goal);
+    if (out_done != nullptr) out_done[r] = goal ? 1 : 0;
+  }
+}
+
+cudaError_t launch_scorer_eval(const simba_scorer_t& sc, const float* obs, const float* next_obs,
+                               int batch, int O, float* out_reward, int32_t* out_done,
+                               float* out_cost, cudaStream_t st) {
+  scorer_eval_kernel<<<(batch + 127) / 128, 128, 0, st>>>(sc, obs, next_obs, batch, O, out_reward,
+                                                           out_done, out_cost);
+  return cudaGetLastError();
+}
+
+// per-row part of compute_objective on materialised trajectories [rows, H+1, O]
+// (simba/policies/mpc_policy.py:30-37, simba/policies/safe_cem_mpc.py:82-93)
+__global__ void score_traj_rows_kernel(simba_scorer_t sc, const float* traj, int rows, int H, int O,
+                                       int objective, float* row_return, uint64_t* row_costmask,
+                                       float* row_costsum) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* base = traj + (long)r * (H + 1) * O;
+  RowScore rs;
+  row_score_init(rs, sc, [&](int b) { return base[b]; });
+  const bool done_first = objective_done_first(objective);
+  for (int t = 0; t < H; ++t) {
+    const float* nx = base + (long)(t + 1) * O;
+    row_score_step(rs, sc, done_first, t, [&](int b) { return nx[b]; });
+  }
+  row_return[r] = rs.cum;
+  row_costmask[r] = rs.cmask;
+  row_costsum[r] = rs.costsum;
+}
+
+cudaError_t launch_score_traj_rows(const simba_scorer_t& sc, const float* traj, int rows, int H,
+                                   int O, int objective, float* row_return, uint64_t* row_costmask,
+                                   float* row_costsum, cudaStream_t st) {
+  score_traj_rows_kernel<<<(rows + 127) / 128, 128, 0, st>>>(sc, traj, rows, H, O, objective,
+                                                             row_return, row_costmask, row_costsum);
+  return cudaGetLastError();
+}
+
+__global__ void pairs_to_scores_kernel(const float* pairs, int n, int objective, float c_max,
+                                       float* out_scores) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 pr = reinterpret_cast<const float2*>(pairs)[i];
+  out_scores[i] = pair_score(objective, pr.x, pr.y, c_max);
+}
+
+cudaError_t launch_pairs_to_scores(const float* pairs, int n, int objective, float c_max,
+                                   float* out_scores, cudaStream_t st) {
+  pairs_to_scores_kernel<<<(n + 255) / 256, 256, 0, st>>>(pairs, n, objective, c_max, out_scores);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// RNG contract probes
+// =============================================================================================
+__global__ void philox_raw_kernel(uint4 ctr, uint2 key, uint32_t* out) {
+  const uint4 r = philox4x32_10(ctr, key);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+cudaError_t launch_philox_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t* out_dev,
+                              cudaStream_t st) {
+  philox_raw_kernel<<<1, 1, 0, st>>>(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]),
+                                     make_uint2(key[0], key[1]), out_dev);
+  return cudaGetLastError();
+}
+
+template <bool kFast>
+__global__ void philox_normals_kernel(uint64_t seed, uint32_t stream, uint32_t iteration,
+                                      uint32_t t, uint32_t s, uint32_t first_row, int n_rows,
+                                      int n_elems, float* out) {
+  const int JB = (n_elems + 3) / 4;
+  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (idx >= (long)n_rows * JB) return;
+  const int row = (int)(idx / JB), j = (int)(idx % JB);
+  const float4 n = philox_normals<kFast>(seed, stream, s, iteration, t, first_row + row, (uint32_t)j);
+  const float z[4] = {n.x, n.y, n.z, n.w};
+  for (int q = 0; q < 4; ++q)
+    if (4 * j + q < n_elems) out[(long)row * n_elems + 4 * j + q] = z[q];
+}
+
+cudaError_t launch_philox_normals(uint64_t seed, int stream, int iteration, int t, int s,
+                                  int first_row, int n_rows, int n_elems, int fast, float* out,
+                                  cudaStream_t st) {
+  const long total = (long)n_rows * ((n_elems + 3) / 4);
+  const int blocks = (int)((total + 255) / 256);
+  if (fast)
+    philox_normals_kernel<true><<<blocks, 256, 0, st>>>(seed, stream, iteration, t, s, first_row,
+                                                        n_rows, n_elems, out);
+  else
+    philox_normals_kernel<false><<<blocks, 256, 0, st>>>(seed, stream, iteration, t, s, first_row,
+                                                         n_rows, n_elems, out);
+  return cudaGetLastError();
+}
+
+}  // namespace simba

@@ -1,0 +1,145 @@
+"""Whole planning call (CemMpc / SafeCemMpc .generate_action) against the oracle's CEM loop with
+identical weights, state and normal draws (north_star parity contract)."""
+import numpy as np
+import pytest
+
+from oracle import philox
+from oracle import simba_oracle as so
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _run_pair(cfg, objective, precision='fp32', member_map='split', over=None, **kw):
+    from simba_b200 import _lib, synthetic
+    c = helpers.workload(cfg, **(over or {}))
+    z, eps, zf = synthetic.make_draws(c['I'], 1, c['N'], c['H'], c['A'], c['P'], c['O'])
+    pol = helpers.cuda_policy(c, objective, precision=precision, member_map=member_map, **kw)
+    pol.set_external_draws(z, eps, zf)
+    action, score = pol.do_generate_action(c['state'])
+    tr = so.Trace()
+    pl_o = helpers.oracle_planner(c, objective, member_map=member_map, **kw)
+    a0, s0, n0 = pl_o.do_generate_action(c['state'], z[:, 0], eps[:, 0], zf[0], tr)
+    mu = pol.buffer(_lib.BUF_MU).cpu().numpy().reshape(c['H'], c['A'])
+    sg = pol.buffer(_lib.BUF_SIGMA).cpu().numpy().reshape(c['H'], c['A'])
+    elite = pol.buffer(_lib.BUF_ELITE, torch.int32).cpu().numpy()
+    return c, pol, (action, score, mu, sg, elite), (a0, s0, n0, tr)
+
+
+@pytest.mark.parametrize("cfg,objective", [('tiny', 'reward'), ('tiny', 'penalty'),
+                                           ('tiny', 'least_cost'), ('tiny', 'feasible_first'),
+                                           ('c1', 'penalty'), ('c1', 'reward')])
+def test_plan_matches_oracle_fp32(cfg, objective):
+    """fp32 path: returns, costs, refit mean/variance within 1e-4 relative; elite indices exact."""
+    c, pol, (action, score, mu, sg, elite), (a0, s0, n0, tr) = _run_pair(cfg, objective)
+    assert int(pol.iterations_run[0]) == n0 == c['I']
+    assert np.array_equal(elite, tr[-1]['elite'])
+    assert np.allclose(mu, tr[-1]['mu'], rtol=1e-4, atol=1e-6)
+    assert np.allclose(sg, tr[-1]['sigma'], rtol=1e-4, atol=1e-6)
+    assert np.isclose(score, s0, rtol=1e-4, atol=1e-5)
+    assert np.allclose(action, a0, rtol=1e-4, atol=1e-6)
+
+
+def test_plan_early_exit_matches_reference_break():
+    """cem_mpc.py:66-67: stop when mean(sigma) <= stddev_threshold, checked after the refit."""
+    c, pol, (action, score, mu, sg, elite), (a0, s0, n0, tr) = _run_pair(
+        'c1', 'penalty', stddev_threshold=0.55)
+    assert 1 <= n0 < c['I']
+    assert int(pol.iterations_run[0]) == n0
+    assert np.allclose(mu, tr[-1]['mu'], rtol=1e-4, atol=1e-6)
+    assert np.allclose(action, a0, rtol=1e-4, atol=1e-6)
+
+
+def test_plan_smoothing_and_member_map_particle():
+    c, pol, (action, score, mu, sg, elite), (a0, s0, n0, tr) = _run_pair(
+        'tiny', 'penalty', member_map='particle', over=dict(E=3), smoothing=0.3)
+    assert np.array_equal(elite, tr[-1]['elite'])
+    assert np.allclose(mu, tr[-1]['mu'], rtol=1e-4, atol=1e-6)
+    assert np.allclose(sg, tr[-1]['sigma'], rtol=1e-4, atol=1e-6)
+
+
+def test_plan_philox_mode_matches_oracle_fed_with_contract_normals():
+    """Production RNG: the device draws Philox normals; the oracle consumes oracle/philox.py's
+    restatement of the same counters. Same decisions, values within 1e-4."""
+    from simba_b200 import _lib
+    c = helpers.workload('tiny')
+    seed = 0x5EED
+    pol = helpers.cuda_policy(c, 'penalty')
+    action, score = pol.do_generate_action(c['state'], seed=seed)
+    B = c['P'] * c['N']
+    z = np.stack([philox.action_normals(seed, it, c['N'], c['H'], c['A']) for it in range(c['I'])])
+    eps = np.stack([philox.noise_normals(seed, it, c['H'], np.arange(B), c['O']) for it in range(c['I'])])
+    zf = philox.final_normals(seed, c['A'])
+    tr = so.Trace()
+    a0, s0, n0 = helpers.oracle_planner(c, 'penalty').do_generate_action(c['state'], z, eps, zf, tr)
+    elite = pol.buffer(_lib.BUF_ELITE, torch.int32).cpu().numpy()
+    assert np.array_equal(elite, tr[-1]['elite'])
+    assert np.allclose(action, a0, rtol=1e-4, atol=1e-5) and np.isclose(score, s0, rtol=1e-4, atol=1e-5)
+    # a different seed gives a different plan; the same seed reproduces bit for bit
+    a1, _ = pol.do_generate_action(c['state'], seed=seed)
+    a2, _ = pol.do_generate_action(c['state'], seed=seed + 1)
+    assert np.array_equal(a1, action) and not np.array_equal(a2, action)
+
+
+def test_batched_states_equal_independent_plans():
+    """configs[3]: S states per call == S independent single-state plans (bit for bit)."""
+    from simba_b200 import synthetic
+    c = helpers.workload('tiny', S=5)
+    pol_b = helpers.cuda_policy(c, 'penalty')
+    acts_b, scores_b = pol_b.do_generate_action(c['state'], seed=11)
+    c1 = dict(c); c1['S'] = 1
+    for s in range(5):
+        pol = helpers.cuda_policy(c1, 'penalty')
+        z = np.stack([philox.action_normals(11, it, c['N'], c['H'], c['A'], state_index=s)
+                      for it in range(c['I'])])[:, None]
+        B = c['P'] * c['N']
+        eps = np.stack([philox.noise_normals(11, it, c['H'], np.arange(B), c['O'], state_index=s)
+                        for it in range(c['I'])])[:, None]
+        zf = philox.final_normals(11, c['A'], state_index=s)[None]
+        pol.set_external_draws(z, eps, zf)
+        a, sc = pol.do_generate_action(c['state'][s])
+        assert np.allclose(a, acts_b[s], rtol=1e-4, atol=1e-5)
+        assert np.isclose(sc, scores_b[s], rtol=1e-4, atol=1e-5)
+
+
+def test_compute_objective_on_materialised_trajectories():
+    """mpc_policy.py:26-39 / safe_cem_mpc.py:76-96 public method."""
+    c = helpers.workload('tiny')
+    rng = np.random.default_rng(3)
+    B = c['P'] * c['N']
+    for objective in ('reward', 'penalty'):
+        pol = helpers.cuda_policy(c, objective)
+        pl_o = helpers.oracle_planner(c, objective)
+        traj = np.tile(c['state'], (B, c['H'] + 1, 1)).astype(np.float32)
+        traj += np.cumsum(rng.normal(0, 0.04, traj.shape), axis=1).astype(np.float32)
+        scores = pol.compute_objective(traj, None)
+        s0, _, _ = pl_o.compute_scores(traj, np.zeros((B, c['H'], c['A']), np.float32))
+        assert np.allclose(scores, s0, rtol=1e-6, atol=1e-6)
+
+
+def test_errors_are_loud():
+    from simba_b200 import SimbaError
+    c = helpers.workload('tiny', E=5)                      # 8*24 = 192 rows, not divisible by 5
+    pol = helpers.cuda_policy(c, 'penalty')
+    with pytest.raises(SimbaError) as e:
+        pol.generate_action(c['state'])
+    assert e.value.code == -2
+    c = helpers.workload('tiny')
+    pol = helpers.cuda_policy(c, 'penalty')
+    with pytest.raises(ValueError):
+        pol.generate_action(np.zeros(7, np.float32))
+
+
+def test_policy_reconstruction_shares_weights():
+    """scripts/tune_cem_policy.py:108-115 re-creates the policy around the same model object."""
+    from simba_b200.policies import CemMpc
+    c = helpers.workload('tiny')
+    pol = helpers.cuda_policy(c, 'reward')
+    a = pol.do_generate_action(c['state'], seed=3)[0]
+    pol2 = CemMpc(pol.model, pol.environment, horizon=c['H'] + 2, iterations=2, smoothing=0.0,
+                  n_samples=c['N'], n_elite=c['K'], particles=c['P'], stddev_threshold=0.0,
+                  noise_stddev=0.01, precision='fp32')
+    b = pol2.do_generate_action(c['state'], seed=3)[0]
+    assert pol2.model.model._handle is pol.model.model._handle
+    assert a.shape == b.shape == (c['A'],) and np.all(np.isfinite(b))

@@ -1,0 +1,112 @@
+"""Host-side mirror of the reference interface (no GPU needed)."""
+import numpy as np
+import pytest
+
+from tests import helpers
+
+
+def test_interface_names_and_kwargs_match_reference():
+    from simba_b200.policies import CemMpc, SafeCemMpc, MpcPolicy, PolicyBase
+    from simba_b200.models import TransitionModel, MlpEnsemble, BaseModel
+    c = helpers.workload('tiny')
+    pol = helpers.cuda_policy(c, 'penalty')
+    assert isinstance(pol, SafeCemMpc) and isinstance(pol, CemMpc) and isinstance(pol, MpcPolicy)
+    assert isinstance(pol, PolicyBase) and isinstance(pol.model, BaseModel)
+    for attr in ('model', 'reward', 'cost', 'action_space', 'horizon', 'n_samples', 'particles',
+                 'iterations', 'smoothing', 'elite', 'stddev_threshold', 'noise_stddev',
+                 'posterior_mean_threashold', 'last_action'):
+        assert hasattr(pol, attr), attr
+    for m in ('generate_action', 'do_generate_action', 'build', 'compute_objective',
+              'optimize_for_safety', 'compute_mean_costs'):
+        assert callable(getattr(pol, m))
+    tm = pol.model
+    for attr in ('inputs_min', 'inputs_max', 'scale_features', 'sampling_propagation',
+                 'observation_space_dim', 'action_space_dim', 'inputs_dim', 'outputs_dim'):
+        assert hasattr(tm, attr), attr
+    for m in ('unfold_sequences', 'simulate_trajectories', 'predict', 'scale', 'fit', 'build', 'save', 'load'):
+        assert callable(getattr(tm, m))
+    assert isinstance(tm.model, MlpEnsemble) and len(tm.model.ensemble) == c['E']
+    w = tm.model.ensemble[0].get_weights()
+    assert len(w) == 2 * c['L'] + 4 and w[0].shape == (c['O'] + c['A'], c['U']) and w[-2].shape == (c['U'], c['O'])
+
+
+def test_sampling_params_bounded_and_unbounded():
+    from simba_b200.policies import MpcPolicy
+    from simba_b200.spaces import Box
+
+    class Env:
+        get_reward = staticmethod(lambda *a: None)
+
+    env = Env(); env.action_space = Box([-1, -2], [1, 4])
+    lb, ub, mu, sd = MpcPolicy(None, env, 3, 4, 5).sampling_params
+    assert list(mu) == [0.0, 1.0] and list(sd) == [1.0, 3.0] and list(lb) == [-1, -2]
+    env.action_space = Box([-np.inf, -1], [np.inf, 1])
+    assert MpcPolicy(None, env, 3, 4, 5).sampling_params == (-100, 100, 0.0, 100)
+
+
+def test_scorer_struct_offsets_for_pointgoal1_and_simple():
+    from simba_b200.environment_utils import ScorerEnvironment, POINTSIMPLEGOAL1_SENSORS
+    sc = ScorerEnvironment()._scorer.scorer_struct()
+    assert (sc.goal_begin, sc.goal_end, sc.goal_dist_index) == (3, 19, -1)
+    assert sc.n_constraints == 1 and (sc.con_begin[0], sc.con_end[0]) == (22, 38)
+    assert abs(sc.con_size[0] - 0.2) < 1e-7 and abs(sc.goal_threshold - 0.24) < 1e-7
+    assert sc.lidar_max_dist == 4.0 and sc.reward_clip == 10.0 and sc.constrain_indicator == 1
+    env = ScorerEnvironment(POINTSIMPLEGOAL1_SENSORS)
+    sc = env._scorer.scorer_struct()
+    assert env.observation_space.shape == (22,)
+    assert (sc.goal_begin, sc.goal_end) == (3, 8) and (sc.con_begin[0], sc.con_end[0]) == (11, 16)
+    env2 = ScorerEnvironment(config=dict(constrain_vases=True))
+    sc2 = env2._scorer.scorer_struct()
+    assert sc2.n_constraints == 2 and (sc2.con_begin[0], sc2.con_end[0]) == (41, 57)   # vases first (:148-151)
+
+
+def test_unsupported_environment_and_activation_are_rejected():
+    from simba_b200 import SimbaError
+    from simba_b200.environment_utils import ScorerEnvironment
+    from simba_b200.models import MlpEnsemble
+    from simba_b200.policies import CemMpc
+    with pytest.raises(SimbaError):
+        MlpEnsemble(62, 60, 2, mlp_params=dict(n_layers=1, units=8, activation='tf.nn.tanh'))
+    with pytest.raises(SimbaError):
+        ScorerEnvironment(config=dict(task='push'))._scorer.scorer_struct()
+
+    class PlainEnv:
+        def __init__(self, env):
+            self.action_space = env.action_space
+            self.observation_space = env.observation_space
+        get_reward = staticmethod(lambda *a: None)
+
+    c = helpers.workload('tiny')
+    pol = helpers.cuda_policy(c, 'reward')
+    bad = CemMpc(pol.model, PlainEnv(pol.environment), 3, 1, 0.0, 8, 2, 2, 0.0, 0.0)
+    with pytest.raises(SimbaError):
+        bad._config()
+
+
+def test_planner_config_is_filled_from_policy_kwargs():
+    from simba_b200 import _lib
+    c = helpers.workload('c1')
+    pol = helpers.cuda_policy(c, 'penalty', precision='bf16', threshold=0.15, smoothing=0.25)
+    cfg = pol._config()
+    assert (cfg.horizon, cfg.iterations, cfg.n_samples, cfg.n_elite, cfg.particles) == (15, 5, 150, 15, 20)
+    assert cfg.objective == _lib.OBJ_SAFE_PENALTY and cfg.precision == _lib.PREC_BF16_TC
+    assert abs(cfg.posterior_mean_threshold - 0.15) < 1e-7 and abs(cfg.smoothing - 0.25) < 1e-7
+    assert list(cfg.act_low)[:2] == [-1.0, -1.0] and list(cfg.init_stddev)[:2] == [1.0, 1.0]
+    assert (cfg.prior_mu, abs(cfg.prior_sigma - 0.27) < 1e-7) == (0.5, True)
+
+
+def test_fit_is_out_of_scope_but_statistics_work():
+    c = helpers.workload('tiny')
+    pol = helpers.cuda_policy(c, 'reward')
+    tm = pol.model
+    with pytest.raises(NotImplementedError):
+        tm.model.fit(np.zeros((4, 62), np.float32), np.zeros((4, 60), np.float32))
+    from simba_b200.environment_utils import ScorerEnvironment
+    from simba_b200.models import TransitionModel
+    env = ScorerEnvironment()
+    tm2 = TransitionModel(tm.model, env.observation_space, env.action_space, True, True)
+    data = np.random.default_rng(0).uniform(-3, 3, (100, 62)).astype(np.float32)
+    tm2._fit_statistics(data)
+    assert np.all(np.isfinite(tm2.inputs_min)) and np.all(np.isfinite(tm2.inputs_max))
+    assert tm2.inputs_min[3] == 0.0 and tm2.inputs_max[3] == 1.0          # lidar bounds kept
+    assert tm2.inputs_min[0] == data[:, 0].min()                          # inf replaced by data min
