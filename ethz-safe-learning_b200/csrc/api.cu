@@ -78,6 +78,8 @@ struct simba_model {
   float* d_w_f32 = nullptr;
   float* d_bias_f32 = nullptr;
   void* d_w_bf16 = nullptr;
+  float* d_bias_tc = nullptr;
+  float tc_scale_a[64] = {0}, tc_scale_b[64] = {0};
   float* d_smin = nullptr;
   float* d_sdelta = nullptr;
   float* d_sinv = nullptr;
@@ -116,7 +118,8 @@ extern "C" int simba_model_create(const simba_model_config_t* cfg, simba_model_t
 }
 
 static void model_free_device(simba_model* m) {
-  cudaFree(m->d_w_f32); cudaFree(m->d_bias_f32); cudaFree(m->d_w_bf16);
+  cudaFree(m->d_w_f32); cudaFree(m->d_bias_f32); cudaFree(m->d_w_bf16); cudaFree(m->d_bias_tc);
+  m->d_bias_tc = nullptr;
   cudaFree(m->d_smin); cudaFree(m->d_sdelta); cudaFree(m->d_sinv);
   m->d_w_f32 = m->d_bias_f32 = m->d_smin = m->d_sdelta = m->d_sinv = nullptr;
   m->d_w_bf16 = nullptr;
@@ -263,6 +266,17 @@ extern "C" int simba_model_commit(simba_model_t* m) {
     m->w_bf16_member_bytes = member_bytes;
     CUDA_TRY(cudaMalloc(&m->d_w_bf16, img.size() * 2));
     CUDA_TRY(cudaMemcpy(m->d_w_bf16, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+    std::vector<float> bt((size_t)E * (L + 1) * 128, 0.0f);
+    for (int e = 0; e < E; ++e) {
+      for (int l = 0; l < L; ++l)
+        for (int n = 0; n < U; ++n) bt[((size_t)e * (L + 1) + l) * 128 + n] = m->biases[e * (L + 2) + l][n];
+      for (int n = 0; n < O; ++n) {
+        bt[((size_t)e * (L + 1) + L) * 128 + n] = m->biases[e * (L + 2) + L][n];
+        bt[((size_t)e * (L + 1) + L) * 128 + 64 + n] = m->biases[e * (L + 2) + L + 1][n];
+      }
+    }
+    CUDA_TRY(cudaMalloc(&m->d_bias_tc, bt.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(m->d_bias_tc, bt.data(), bt.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
 
   // ---- scaler: delta = max - min, 1.01 where delta < 1e-5 (transition_model.py:85-86) ----------
@@ -272,6 +286,10 @@ extern "C" int simba_model_commit(simba_model_t* m) {
     if (d < 1e-5f) d = 1.01f;
     delta[k] = d;
     inv[k] = 1.0f / d;
+  }
+  for (int k = 0; k < 64; ++k) {
+    m->tc_scale_a[k] = k < IN ? (m->scale_on ? inv[k] : 1.0f) : 0.0f;
+    m->tc_scale_b[k] = k < IN ? (m->scale_on ? -m->smin[k] * inv[k] : 0.0f) : 0.0f;
   }
   CUDA_TRY(cudaMalloc(&m->d_smin, IN * sizeof(float)));
   CUDA_TRY(cudaMalloc(&m->d_sdelta, IN * sizeof(float)));
@@ -293,6 +311,10 @@ static void fill_model_params(const simba_model* m, RolloutParams& prm) {
   prm.act_rows = m->act_rows;
   prm.w_bf16 = m->d_w_bf16;
   prm.w_bf16_member_bytes = m->w_bf16_member_bytes;
+  prm.bias_tc = m->d_bias_tc;
+  memcpy(prm.tc_scale_a, m->tc_scale_a, sizeof(prm.tc_scale_a));
+  memcpy(prm.tc_scale_b, m->tc_scale_b, sizeof(prm.tc_scale_b));
+  prm.tc_tiles_per_cta = 1;
   prm.smin = m->d_smin;
   prm.sdelta = m->d_sdelta;
   prm.sinv = m->d_sinv;
@@ -331,13 +353,20 @@ static int build_geom(int S, int P, int N, int world, int rank, int H, int O, in
   return SIMBA_OK;
 }
 
-static void build_tiles(const RowGeom& g, int tile_rows, std::vector<Tile>& tiles) {
+// `group` > 1 pads every member's tile run with empty tiles to a multiple of `group`, so that a CTA
+// that takes `group` consecutive tiles never mixes members (its weights are one member's).
+static void build_tiles(const RowGeom& g, int tile_rows, std::vector<Tile>& tiles, int group = 1) {
   tiles.clear();
   for (int e = 0; e < g.E; ++e) {
     const long total = (long)g.S * g.rows_per_state[e];
     for (long k0 = 0; k0 < total; k0 += tile_rows) {
       Tile t;
       t.member = e; t.k0 = (int)k0; t.count = (int)std::min<long>(tile_rows, total - k0); t.pad = 0;
+      tiles.push_back(t);
+    }
+    while (tiles.size() % group) {
+      Tile t;
+      t.member = e; t.k0 = 0; t.count = 0; t.pad = 0;
       tiles.push_back(t);
     }
   }
@@ -406,6 +435,7 @@ struct simba_planner {
   std::vector<Tile> tiles;
   Tile* d_tiles = nullptr;
   int tile_rows = 0;
+  int tiles_per_cta = 1;
   int c_max = -1;
   // workspace
   float *actions = nullptr, *row_ret = nullptr, *row_csum = nullptr, *pairs_local = nullptr,
@@ -535,6 +565,11 @@ extern "C" int simba_planner_create(simba_model_t* model, const simba_planner_co
   if (rc != SIMBA_OK) { delete p; return rc; }
   p->tile_rows = cfg->precision == SIMBA_PREC_BF16_TC ? kTcTileRows : kF32TileRows;
   build_tiles(p->geom, p->tile_rows, p->tiles);
+  if (cfg->precision == SIMBA_PREC_BF16_TC && p->tiles.size() > 148) {
+    // more tiles than SMs: two tiles per CTA so one tile's MMAs overlap the other's epilogue
+    p->tiles_per_cta = 2;
+    build_tiles(p->geom, p->tile_rows, p->tiles, 2);
+  }
   p->c_max = beta_count_threshold(cfg->particles, cfg->posterior_mean_threshold, cfg->prior_mu,
                                   cfg->prior_sigma);
 
@@ -676,6 +711,7 @@ static int do_rollout_score(simba_planner_t* p, const float* states, const float
   prm.objective = p->cfg.objective;
   prm.active = active;
   prm.row_return = row_return; prm.row_costmask = row_costmask; prm.row_costsum = row_costsum;
+  prm.tc_tiles_per_cta = p->tiles_per_cta;
   if (p->cfg.precision == SIMBA_PREC_BF16_TC)
     CUDA_TRY(launch_rollout_tc(prm, prm.n_tiles, (cudaStream_t)stream));
   else

@@ -168,11 +168,12 @@ def test_sample_actions_bit_exact_and_philox(lib):
     sg = rng.uniform(0.1, 1.0, (1, H, A)).astype(np.float32)
     z = rng.standard_normal((1, N, H, A)).astype(np.float32)
     out = torch.empty((1, N, H, A), dtype=torch.float32, device='cuda')
-    _lib.check(lib.simba_sample_actions(pl, P(dev(mu)), P(dev(sg)), P(dev(z)), 0, 0, None, P(out), None))
+    d_mu, d_sg, d_z = dev(mu), dev(sg), dev(z)           # keep the device copies alive across the launch
+    _lib.check(lib.simba_sample_actions(pl, P(d_mu), P(d_sg), P(d_z), 0, 0, None, P(out), None))
     ref = np.minimum(np.maximum(z * sg + mu, np.float32(-1)), np.float32(1))
     assert np.array_equal(out.cpu().numpy(), ref)
     assert (ref == 1.0).sum() > 0 and (ref == -1.0).sum() > 0        # clipping exercised
-    _lib.check(lib.simba_sample_actions(pl, P(dev(mu)), P(dev(sg)), None, 99, 2, None, P(out), None))
+    _lib.check(lib.simba_sample_actions(pl, P(d_mu), P(d_sg), None, 99, 2, None, P(out), None))
     zz = philox.action_normals(99, 2, N, H, A)[None]
     ref = np.minimum(np.maximum(zz * sg + mu, np.float32(-1)), np.float32(1))
     assert np.max(np.abs(out.cpu().numpy() - ref)) < 5e-6
@@ -224,7 +225,8 @@ def test_rollout_score_rows_match_oracle(lib, cfg, objective, member_map, over):
     ret = torch.empty(B, dtype=torch.float32, device='cuda')
     mask = torch.empty(B, dtype=torch.int64, device='cuda')
     csum = torch.empty(B, dtype=torch.float32, device='cuda')
-    _lib.check(lib.simba_rollout_score(pl, P(dev(c['state'][None])), P(dev(acts[None])), P(dev(eps[None])),
+    d_state, d_acts, d_eps = dev(c['state'][None]), dev(acts[None]), dev(eps[None])
+    _lib.check(lib.simba_rollout_score(pl, P(d_state), P(d_acts), P(d_eps),
                                        0, 0, None, P(ret), P(mask), P(csum), None))
     torch.cuda.synchronize()
     traj, cum0, mask0, csum0 = _oracle_rows(c, pl_o, acts, eps, objective)
@@ -260,8 +262,9 @@ def test_score_reduce_select_refit_pipeline(lib):
             mask |= row_mask[:, :, t].astype(np.uint64) << np.uint64(t)
         row_csum = row_mask.sum(-1).astype(np.float32)
         pairs = torch.empty((N, 2), dtype=torch.float32, device='cuda')
-        _lib.check(lib.simba_score_reduce(pl, P(dev(row_ret)), P(dev(mask.view(np.int64))), P(dev(row_csum)),
-                                          None, P(pairs), None))
+        d_ret, d_mask, d_csum = dev(row_ret), dev(mask.view(np.int64)), dev(row_csum)
+        _lib.check(lib.simba_score_reduce(pl, P(d_ret), P(d_mask), P(d_csum), None, P(pairs), None))
+        torch.cuda.synchronize()
         ret0 = row_ret.sum(0, dtype=np.float32) / np.float32(P_)
         counts = row_mask.sum(0).max(-1).astype(np.float32)
         cost0 = dict(reward=np.zeros(N, np.float32), least_cost=row_csum.sum(0, dtype=np.float32) / np.float32(P_)
