@@ -7,16 +7,25 @@
 //
 //   * one CTA = one ensemble member x NTILES row tiles of 128 rollouts; the member's whole bf16
 //     weight set (144 KB for 4x128) is staged ONCE in shared memory by the TMA engine
-//     (cp.async.bulk, pre-swizzled UMMA images) and reused for all H steps x (L+1) layers;
-//   * activations are the A operand: each epilogue thread owns one rollout row, reads its fp32
-//     accumulator row from TMEM (tcgen05.ld 32x32b), applies bias + ReLU, packs bf16 and stores the
-//     row straight into the 128B-swizzled K-major A tile of the next layer;
+//     (cp.async.bulk of pre-swizzled UMMA images) and reused for all H steps x (L+1) layers;
+//   * activations are the A operand. Q epilogue threads share one rollout row (Q = 4: latency
+//     configuration for small populations, Q = 2 with two tiles per CTA: throughput configuration):
+//     each reads its column slice of the fp32 accumulator row from TMEM (tcgen05.ld 32x32b), applies
+//     bias + ReLU, packs bf16 and stores straight into the 128B-swizzled K-major A tile of the next
+//     layer; the thread count per SM sub-partition (4 warps) is what hides the MUFU / TMEM latencies;
 //   * one elected thread issues tcgen05.mma (M=128, N=128, K=16 per instruction, fp32 accumulate in
 //     TMEM) and tcgen05.commit; two mbarriers per tile (A ready / accumulator ready) are the only
-//     synchronisation, so with NTILES=2 the MMAs of one tile overlap the epilogue of the other;
-//   * the Gaussian head epilogue does softplus, sqrt, Philox4x32-10 + Box-Muller, the residual
-//     state update, and the lidar reward / hazard cost on registers; states never leave the SM.
+//     CTA-level synchronisation, so with two tiles the MMAs of one overlap the epilogue of the other;
+//   * the rollout state s_t (fp32) lives in spare TMEM columns next to the accumulators, so it costs
+//     no registers between steps. The Gaussian-head epilogue is ONE pass over 16-wide column chunks:
+//     load mu / raw-var accumulators and the state chunk from TMEM, softplus, sqrt, Philox4x32-10 +
+//     Box-Muller, residual update, store the state back (tcgen05.st), and in the same registers
+//     pack the scaled bf16 input of the NEXT step into the A tile and take the partial lidar minima.
+//     The per-row min over slices owned by different threads goes through a small shared-memory
+//     exchange and one named barrier per step and tile.
 #include <cuda_bf16.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 #include "rollout_params.cuh"
@@ -25,9 +34,10 @@ namespace simba {
 
 namespace {
 
-constexpr int kU = 128;          // hidden width this kernel covers
-constexpr int kMaxO = 60;        // observation dims held in registers
+constexpr int kU = 128;                 // hidden width this kernel covers
+constexpr int kMaxO = 60;               // observation dims (two Gaussian heads padded to 2 x 64 columns)
 constexpr int kAtomBytes = 128 * 128;   // one 64-wide K atom of a 128-row tile (bf16, SW128)
+constexpr int kParts = 1 + SIMBA_MAX_CONSTRAINTS;   // goal + constrained lidar partial minima
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -43,23 +53,26 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
 }
+// suspend-time hint: the waiting warp sleeps in hardware until the phase completes (or this many
+// ns pass), instead of burning issue slots in a polling loop next to the working warps
+constexpr uint32_t kSuspendHintNs = 100000;
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(kSuspendHintNs)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must fault the kernel, never hang the GPU.
+// Bounded wait: a protocol bug must fault the kernel, never hang the GPU. try_wait suspends the
+// warp in hardware for a bounded time, so the spin count is the only bookkeeping on the slow path.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
+    if (++spins > (1u << 20)) __trap();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() {
@@ -104,7 +117,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
 }
-// 32 lanes x 32 consecutive fp32 columns: thread i gets row (lane base + i)
+// 32 lanes x 32 (16) consecutive fp32 columns: thread i gets row (lane base + i)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -118,8 +131,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 // relu(a), relu(b) -> packed bf16x2 (a in the low half)
 __device__ __forceinline__ uint32_t pack_relu_bf16(float a, float b) {
@@ -132,10 +166,26 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
+// packed fp32x2 add (FADD2): one issue slot for two bias adds
+__device__ __forceinline__ float2 add2(uint32_t lo, uint32_t hi, float2 b) {
+  unsigned long long a = ((unsigned long long)hi << 32) | lo, bb, r;
+  bb = ((unsigned long long)__float_as_uint(b.y) << 32) | __float_as_uint(b.x);
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(bb));
+  return make_float2(__uint_as_float((uint32_t)r), __uint_as_float((uint32_t)(r >> 32)));
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
                                              uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
                : "memory");
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+template <int kThreads>
+__device__ __forceinline__ void named_bar_sync(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kThreads) : "memory");
 }
 
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (dense 128 B rows)
@@ -151,7 +201,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
-// softplus on the MUFU path, accurate for very negative inputs (var head biases of trained models)
+// softplus on the MUFU path, accurate for very negative inputs (var-head biases of trained models)
 __device__ __forceinline__ float softplus_fast(float x) {
   const float e = __expf(fminf(x, 30.0f));
   const float small = e * (1.0f - e * (0.5f - e * 0.33333334f));
@@ -160,25 +210,39 @@ __device__ __forceinline__ float softplus_fast(float x) {
   return x > 15.0f ? x : sp;
 }
 
+// Box-Muller on the MUFU path (same counter map and uniforms as the accurate path in common.cuh)
+__device__ __forceinline__ float4 normals4_fast(uint4 b) {
+  const float ua = u01(b.x), ub = u01(b.y), uc = u01(b.z), ud = u01(b.w);
+  const float ra = sqrt_approx(-1.3862943611198906f * __log2f(ua));
+  const float rb = sqrt_approx(-1.3862943611198906f * __log2f(uc));
+  float sa, ca, sb, cb;
+  __sincosf(6.283185307179586f * ub, &sa, &ca);
+  __sincosf(6.283185307179586f * ud, &sb, &cb);
+  return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
+}
+
 struct TileInfo {
   int32_t member, k0, count, valid;
 };
 
 }  // namespace
 
-// kPG1: compile-time PointGoal1 layout (O=60, A=2, goal_lidar [3,19), one constrained lidar
-// [22,38)) so that the lidar reductions index the register-resident state statically. The generic
-// instantiation handles any O <= 60, O + A <= 64 with predicated (slower) scoring.
-template <int NTILES, bool kPG1>
-__global__ void __launch_bounds__(NTILES * 128 + 32, 1) rollout_tc_kernel(const RolloutParams prm) {
+// NTILES row tiles per CTA, Q epilogue threads per rollout row.
+template <int NTILES, int Q>
+__global__ void __launch_bounds__(NTILES* Q * 128 + 32, 1) rollout_tc_kernel(const RolloutParams prm) {
+  constexpr int kTileThreads = Q * 128;
+  constexpr int kEpiThreads = NTILES * kTileThreads;
+  constexpr int OW = 64 / Q;          // head outputs (= state dims = layer-0 K elements) per thread
+  constexpr int HC = 4 / Q;           // 32-column accumulator chunks per thread in hidden layers
+  // TMEM columns: NTILES x 128 accumulator columns, then NTILES x 64 state columns (power of two)
+  constexpr int kTmemCols = (NTILES * 192 <= 256) ? 256 : 512;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const RowGeom& g = prm.g;
   const int L = prm.L;
   const int H = g.H;
-  const int O = kPG1 ? 60 : g.O;
-  const int A = kPG1 ? 2 : g.A;
+  const int O = g.O, A = g.A;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kCtrlWarp = NTILES * 4;
+  constexpr int kCtrlWarp = NTILES * Q * 4;
   const bool is_ctrl = warp == kCtrlWarp;
 
   // ---- shared memory carve-up (base is 1024-aligned: required by SWIZZLE_128B) -------------------
@@ -186,7 +250,10 @@ __global__ void __launch_bounds__(NTILES * 128 + 32, 1) rollout_tc_kernel(const 
   uint8_t* w_smem = smem_raw;
   uint8_t* a_smem = w_smem + w_bytes;                                      // [NTILES][2 atoms]
   float* bias_smem = reinterpret_cast<float*>(a_smem + NTILES * 2 * kAtomBytes);   // [(L+1)][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_smem + (L + 1) * 128);
+  float* scale_smem = bias_smem + (L + 1) * 128;                           // [2][64]: a, b of x*a+b
+  float* pen_smem = scale_smem + 128;                                      // [kParts][64]: 0 in slice, +inf outside
+  float* part_smem = pen_smem + kParts * 64;                               // [NTILES][Q][kParts][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part_smem + NTILES * Q * kParts * 128);
   // bars[0] = weights landed; bars[1 + j] = A ready (tile j); bars[1 + NTILES + j] = accumulator ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * NTILES);
   TileInfo* tinfo = reinterpret_cast<TileInfo*>(tmem_slot + 2);
@@ -203,7 +270,7 @@ __global__ void __launch_bounds__(NTILES * 128 + 32, 1) rollout_tc_kernel(const 
     mbar_init(bar_w, 1);
 #pragma unroll
     for (int j = 0; j < NTILES; ++j) {
-      mbar_init(bar_a[j], 4);        // one arrival per epilogue warp of the tile
+      mbar_init(bar_a[j], 4 * Q);    // one arrival per epilogue warp of the tile
       mbar_init(bar_acc[j], 1);      // tcgen05.commit
     }
     fence_barrier_init();
@@ -224,7 +291,7 @@ __global__ void __launch_bounds__(NTILES * 128 + 32, 1) rollout_tc_kernel(const 
     }
     tinfo[threadIdx.x] = info;
   }
-  if (is_ctrl) tmem_alloc(smem_u32(tmem_slot), NTILES * 128);
+  if (is_ctrl) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -236,8 +303,11 @@ __global__ void __launch_bounds__(NTILES * 128 + 32, 1) rollout_tc_kernel(const 
   for (int j = 0; j < NTILES; ++j)
     if (tinfo[j].valid) { any_valid = true; member = tinfo[j].member; }
 
-  if (any_valid) {
-    if (is_ctrl) {
+  // (setmaxnreg register re-balancing between the control warp and the epilogue warpgroups was
+  //  tried and faulted at run time on sm_100a / CUDA 12.9; with the state in TMEM 96 registers
+  //  per thread are enough, so the kernel runs with the plain launch-bound allocation.)
+  if (warp >= kCtrlWarp) {
+    if (any_valid && is_ctrl) {
       // =========================== control warp: TMA + MMA issue ===============================
       if (lane == 0) {
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(prm.w_bf16) +
@@ -277,100 +347,238 @@ __global__ void __launch_bounds__(NTILES * 128 + 32, 1) rollout_tc_kernel(const 
         }
       }
       __syncwarp();
-    } else {
-      // =========================== epilogue warps: one thread = one rollout row ==================
-      const int j = warp >> 2;                 // tile of this warp
-      const int r = threadIdx.x - j * 128;     // row in tile == TMEM lane
+    }
+  } else {
+    if (any_valid) {
+      // ============ epilogue warps: Q threads per rollout row, each owns a column slice ============
+      const int j = warp / (4 * Q);                       // tile of this warp
+      const int wl = warp - j * 4 * Q;                    // warp within the tile
+      const int cgp = wl >> 2;                            // column group in [0, Q)
+      const int r = (wl & 3) * 32 + lane;                 // row in tile == TMEM lane
       const TileInfo ti = tinfo[j];
-      // biases of this member -> shared (all epilogue threads of the CTA cooperate)
+      // biases + scaler of this member -> shared (all epilogue threads of the CTA cooperate)
       {
         const float* bsrc = prm.bias_tc + (size_t)member * (L + 1) * 128;
-        for (int i = threadIdx.x; i < (L + 1) * 128; i += NTILES * 128) bias_smem[i] = bsrc[i];
-        asm volatile("bar.sync 1, %0;" ::"n"(NTILES * 128));
+        for (int i = threadIdx.x; i < (L + 1) * 128; i += kEpiThreads) bias_smem[i] = bsrc[i];
+        for (int i = threadIdx.x; i < 64; i += kEpiThreads) {
+          scale_smem[i] = prm.tc_scale_a[i];
+          scale_smem[64 + i] = prm.tc_scale_b[i];
+          const simba_scorer_t& scc = prm.scorer;
+          pen_smem[i] = (i >= scc.goal_begin && i < scc.goal_end) ? 0.0f : INFINITY;
+          for (int q = 0; q < SIMBA_MAX_CONSTRAINTS; ++q)
+            pen_smem[(1 + q) * 64 + i] =
+                (q < scc.n_constraints && i >= scc.con_begin[q] && i < scc.con_end[q]) ? 0.0f : INFINITY;
+        }
+        named_bar_sync<kEpiThreads>(1);
       }
       if (ti.valid) {
         const bool row_ok = r < ti.count;
         const RowId id = decode_row(g, ti.member, ti.k0 + (row_ok ? r : 0));
         const uint64_t seed = prm.seed_ptr ? *prm.seed_ptr : prm.seed;
-        const uint32_t a_tile = smem_u32(a_smem + j * 2 * kAtomBytes);
-        const uint32_t a_row = a_tile + (uint32_t)r * 128;
+        const uint32_t a_row = smem_u32(a_smem + j * 2 * kAtomBytes) + (uint32_t)r * 128;
         const uint32_t swz = (uint32_t)(r & 7);
-        const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)j * 128;
+        const uint32_t t_lane = tmem_base + ((uint32_t)((wl & 3) * 32) << 16) + (uint32_t)j * 128;
         const float* act_ptr = prm.actions + ((int64_t)id.s * g.N + id.i_global) * prm.action_stride;
-        const float* sc_a = prm.tc_scale_a;     // x_scaled = fma(x, sc_a, sc_b)
-        const float* sc_b = prm.tc_scale_b;
         const bool done_first = objective_done_first(prm.objective);
         const simba_scorer_t& sc = prm.scorer;
+        const int o_base = cgp * OW;                      // first state dim / head output of this thread
+        float* part = part_smem + ((j * Q + cgp) * kParts) * 128 + r;         // [kParts] stride 128
+        const float* part_row = part_smem + (j * Q * kParts) * 128 + r;       // group 0 base of this row
+        const float D = sc.lidar_max_dist;
 
-        float s[kMaxO];
-        {
-          const float* sp = prm.states + (prm.state_per_row ? id.r_global : (int64_t)id.s) * prm.state_stride;
+        const uint32_t t_state = tmem_base + ((uint32_t)((wl & 3) * 32) << 16) +
+                                 (uint32_t)(NTILES * 128 + j * 64);            // this row's state columns
+        const float* s0_ptr = prm.states + (prm.state_per_row ? id.r_global : (int64_t)id.s) * prm.state_stride;
+        const float* bh = bias_smem + L * 128;
+
+        // Which of this thread's 16-wide chunks intersect the goal slice / constrained slices
+        // (warp-uniform bit masks, bit = sub-chunk), so that chunks outside every lidar do no scoring.
+        uint32_t has_goal = 0, has_con = 0;
 #pragma unroll
-          for (int o = 0; o < kMaxO; ++o) s[o] = (row_ok && o < O) ? sp[o] : 0.0f;
+        for (int sub = 0; sub < OW / 16; ++sub) {
+          const int lo = o_base + sub * 16, hi = lo + 16;
+          if (sc.goal_dist_index >= 0 ? (sc.goal_dist_index >= lo && sc.goal_dist_index < hi)
+                                      : (sc.goal_begin < hi && sc.goal_end > lo)) has_goal |= 1u << sub;
+          for (int q = 0; q < sc.n_constraints; ++q)
+            if (sc.con_begin[q] < hi && sc.con_end[q] > lo) has_con |= 1u << (sub * SIMBA_MAX_CONSTRAINTS + q);
         }
-        // static-index state access for the scorer
-        auto closest = [&](int begin, int end, float D) {
-          float best = INFINITY;
+
+        // One pass over this thread's OW state dims in 16-wide chunks. kFirst: load s_0 from global
+        // memory; otherwise apply the Gaussian-head update of step t (mlp_ensemble.py:189-193,
+        // transition_model.py:75). Either way: store the state to TMEM, write the scaled bf16 input
+        // of step t_next into the layer-0 A tile (transition_model.py:72,79-87) and publish the
+        // partial lidar minima (closest_distance, safety_gym.py:188-192).
+        auto state_pass = [&](auto first_tag, auto sample_tag, int t, int t_next) {
+          constexpr bool kFirst = decltype(first_tag)::value;
+          constexpr bool kSample = decltype(sample_tag)::value;
+          float gmin = INFINITY;
+          float cmin[SIMBA_MAX_CONSTRAINTS];
 #pragma unroll
-          for (int o = 0; o < kMaxO; ++o) {
-            if (kPG1 ? (o >= begin && o < end) : true) {
-              float v = __fsub_rn(D, __fmul_rn(D, __fsub_rn(1.0f, s[o])));
-              v = fminf(fmaxf(v, 0.0f), D);
-              if (kPG1) best = fminf(best, v);
-              else best = (o >= begin && o < end) ? fminf(best, v) : best;
+          for (int q = 0; q < SIMBA_MAX_CONSTRAINTS; ++q) cmin[q] = INFINITY;
+          const float* ep = nullptr;
+          if (!kFirst && kSample && prm.eps != nullptr)
+            ep = prm.eps + (((int64_t)id.s * H + t) * ((int64_t)g.P * g.N) + id.r_global) * O;
+#pragma unroll
+          for (int sub = 0; sub < OW / 16; ++sub) {
+            const int oc = o_base + sub * 16;               // first state dim of this chunk
+            const bool full = oc + 16 <= O;                 // warp-uniform: no padding / action columns
+            float sv[16];
+            if (kFirst) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) sv[i] = (row_ok && oc + i < O) ? s0_ptr[oc + i] : 0.0f;
+            } else {
+              uint32_t vm[16], vv[16], st[16];
+              tmem_ld16(t_lane + oc, vm);
+              if (kSample) tmem_ld16(t_lane + 64 + oc, vv);
+              tmem_ld16(t_state + oc, st);
+              tmem_ld_wait();
+#pragma unroll
+              for (int jb = 0; jb < 4; ++jb) {
+                const int o0 = oc + jb * 4;
+                const float4 bm = *reinterpret_cast<const float4*>(bh + o0);
+                const float bmu[4] = {bm.x, bm.y, bm.z, bm.w};
+                float d[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) d[q] = __uint_as_float(vm[jb * 4 + q]) + bmu[q];
+                if (kSample && o0 < O) {
+                  float e4[4] = {0.f, 0.f, 0.f, 0.f};
+                  if (ep != nullptr) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                      if (o0 + q < O) e4[q] = ep[o0 + q];
+                  } else {
+                    const uint4 bits = philox4x32_10(
+                        make_uint4((uint32_t)(o0 >> 2), (uint32_t)id.r_global,
+                                   (uint32_t)t | ((uint32_t)prm.iteration << 16),
+                                   (uint32_t)id.s | (kStreamNoise << 28)), philox_key(seed));
+                    const float4 z = normals4_fast(bits);
+                    e4[0] = z.x; e4[1] = z.y; e4[2] = z.z; e4[3] = z.w;
+                  }
+                  const float4 bv = *reinterpret_cast<const float4*>(bh + 64 + o0);
+                  const float bvar[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const float var = softplus_fast(__uint_as_float(vv[jb * 4 + q]) + bvar[q]) + 1e-4f;
+                    d[q] = fmaf(sqrt_approx(var), e4[q], d[q]);
+                  }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float old = __uint_as_float(st[jb * 4 + q]);
+                  sv[jb * 4 + q] = (full || o0 + q < O) ? old + d[q] : old;
+                }
+              }
+            }
+            {
+              uint32_t st[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) st[i] = __float_as_uint(sv[i]);
+              tmem_st16(t_state + oc, st);
+            }
+            // ---- partial lidar minima, only for chunks that intersect a slice -----------------
+            const uint32_t con_bits = (has_con >> (sub * SIMBA_MAX_CONSTRAINTS)) & 0xFu;
+            if (((has_goal >> sub) & 1u) | con_bits) {
+              if (sc.goal_dist_index >= 0) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (oc + i == sc.goal_dist_index) gmin = fmaxf(sv[i], 0.0f);  // safety_gym.py:172-174
+              }
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float w = __fsub_rn(D, __fmul_rn(D, __fsub_rn(1.0f, sv[i])));
+                v[i] = fminf(fmaxf(w, 0.0f), D);
+              }
+              // pen[k][o] = 0 inside slice k, +inf outside: min(v + pen) is the slice minimum
+              if (((has_goal >> sub) & 1u) && sc.goal_dist_index < 0) {
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                  const float4 pn = *reinterpret_cast<const float4*>(pen_smem + oc + i4 * 4);
+                  gmin = fminf(gmin, fminf(fminf(v[i4 * 4] + pn.x, v[i4 * 4 + 1] + pn.y),
+                                           fminf(v[i4 * 4 + 2] + pn.z, v[i4 * 4 + 3] + pn.w)));
+                }
+              }
+#pragma unroll
+              for (int q = 0; q < SIMBA_MAX_CONSTRAINTS; ++q) {
+                if ((con_bits >> q) & 1u) {
+#pragma unroll
+                  for (int i4 = 0; i4 < 4; ++i4) {
+                    const float4 pn = *reinterpret_cast<const float4*>(pen_smem + (1 + q) * 64 + oc + i4 * 4);
+                    cmin[q] = fminf(cmin[q], fminf(fminf(v[i4 * 4] + pn.x, v[i4 * 4 + 1] + pn.y),
+                                                   fminf(v[i4 * 4 + 2] + pn.z, v[i4 * 4 + 3] + pn.w)));
+                  }
+                }
+              }
+            }
+            // ---- scaled bf16 input of the next step ---------------------------------------------
+            if (t_next < H) {
+              float x[16];
+              if (full) {
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                  const float4 sa = *reinterpret_cast<const float4*>(scale_smem + oc + i4 * 4);
+                  const float4 sb = *reinterpret_cast<const float4*>(scale_smem + 64 + oc + i4 * 4);
+                  x[i4 * 4 + 0] = fmaf(sv[i4 * 4 + 0], sa.x, sb.x);
+                  x[i4 * 4 + 1] = fmaf(sv[i4 * 4 + 1], sa.y, sb.y);
+                  x[i4 * 4 + 2] = fmaf(sv[i4 * 4 + 2], sa.z, sb.z);
+                  x[i4 * 4 + 3] = fmaf(sv[i4 * 4 + 3], sa.w, sb.w);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const int o = oc + i;
+                  float xin = sv[i];                                             // zero beyond O
+                  if (o >= O && o < O + A) xin = row_ok ? act_ptr[t_next * A + (o - O)] : 0.0f;
+                  x[i] = fmaf(xin, scale_smem[o], scale_smem[64 + o]);           // padded k: a = b = 0
+                }
+              }
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                const uint32_t chunk = (uint32_t)(oc / 8 + c);
+                st_shared_v4(a_row + ((chunk ^ swz) << 4), pack_bf16(x[8 * c], x[8 * c + 1]),
+                             pack_bf16(x[8 * c + 2], x[8 * c + 3]), pack_bf16(x[8 * c + 4], x[8 * c + 5]),
+                             pack_bf16(x[8 * c + 6], x[8 * c + 7]));
+              }
             }
           }
-          return best;
-        };
-        auto goal_dist = [&]() {
-          if (kPG1) return closest(3, 19, sc.lidar_max_dist);
-          if (sc.goal_dist_index >= 0) {
-            float v = 0.0f;
-#pragma unroll
-            for (int o = 0; o < kMaxO; ++o) v = (o == sc.goal_dist_index) ? s[o] : v;
-            return fmaxf(v, 0.0f);
+          tmem_st_wait();
+          if (t_next < H) {                      // hand the next step's input to the tensor core first
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a[j]);
           }
-          return closest(sc.goal_begin, sc.goal_end, sc.lidar_max_dist);
+          part[0] = gmin;
+#pragma unroll
+          for (int q = 0; q < SIMBA_MAX_CONSTRAINTS; ++q)
+            if (q < sc.n_constraints) part[(1 + q) * 128] = cmin[q];
         };
-        auto cost_now = [&]() {
-          if (kPG1) return closest(22, 38, sc.lidar_max_dist) <= sc.con_size[0] ? 1.0f : 0.0f;
-          float c = 0.0f;
-          for (int q = 0; q < sc.n_constraints; ++q)
-            c += closest(sc.con_begin[q], sc.con_end[q], sc.lidar_max_dist) <= sc.con_size[q] ? 1.0f : 0.0f;
-          return sc.constrain_indicator ? (c > 0.0f ? 1.0f : 0.0f) : c;
+        // combine the Q partials of this row (group-0 thread only): goal distance and cost(s)
+        auto combine = [&](float& dist, float& cost) {
+          float gmin = INFINITY;
+#pragma unroll
+          for (int c = 0; c < Q; ++c) gmin = fminf(gmin, part_row[(c * kParts) * 128]);
+          float cst = 0.0f;
+          for (int q = 0; q < sc.n_constraints; ++q) {
+            float m = INFINITY;
+#pragma unroll
+            for (int c = 0; c < Q; ++c) m = fminf(m, part_row[(c * kParts + 1 + q) * 128]);
+            cst += (m <= sc.con_size[q]) ? 1.0f : 0.0f;
+          }
+          dist = gmin;
+          cost = sc.constrain_indicator ? (cst > 0.0f ? 1.0f : 0.0f) : cst;
         };
+
         RowScore rs;
-        rs.cum = 0.0f; rs.costsum = 0.0f; rs.cmask = 0ull; rs.done = false;
-        rs.dist = goal_dist();
-        rs.cost = cost_now();
+        rs.cum = 0.0f; rs.costsum = 0.0f; rs.cmask = 0ull; rs.done = false; rs.dist = 0.0f; rs.cost = 0.0f;
+        state_pass(std::true_type{}, std::false_type{}, 0, 0);
+        named_bar_sync<kTileThreads>(2 + j);
+        if (cgp == 0) combine(rs.dist, rs.cost);
+        // (the partials are next written after L+1 accumulator waits, each of which needs an A-ready
+        //  arrival from every warp of the tile, including the group-0 warps reading here)
 
         uint32_t ph = 0;
         for (int t = 0; t < H; ++t) {
-          // ---- layer-0 A operand: bf16(scale([s_t, a_t])), 64 K-elements = 8 swizzled 16B chunks --
-          {
-            float x[64];
-#pragma unroll
-            for (int k = 0; k < 64; ++k) {
-              float v = 0.0f;
-              if (k < kMaxO) v = s[k];
-              if (!kPG1) {
-                if (k >= O && k < O + A) v = row_ok ? act_ptr[t * A + (k - O)] : 0.0f;
-              } else if (k >= 60 && k < 62) {
-                v = row_ok ? act_ptr[t * 2 + (k - 60)] : 0.0f;
-              }
-              x[k] = fmaf(v, sc_a[k], sc_b[k]);      // padded k: sc_a = sc_b = 0
-            }
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-              st_shared_v4(a_row + (((uint32_t)c ^ swz) << 4), pack_bf16(x[8 * c], x[8 * c + 1]),
-                           pack_bf16(x[8 * c + 2], x[8 * c + 3]), pack_bf16(x[8 * c + 4], x[8 * c + 5]),
-                           pack_bf16(x[8 * c + 6], x[8 * c + 7]));
-          }
-          tc_fence_before();
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_a[j]);
-
           // ---- hidden layers: TMEM -> +bias, ReLU, bf16 -> next A operand -----------------------
           for (int l = 0; l < L; ++l) {
             mbar_wait(bar_acc[j], ph);
@@ -378,7 +586,8 @@ __global__ void __launch_bounds__(NTILES * 128 + 32, 1) rollout_tc_kernel(const 
             tc_fence_after();
             const float* bl = bias_smem + l * 128;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int cc = 0; cc < HC; ++cc) {
+              const int c = cgp * HC + cc;                 // 32-column chunk of the accumulator row
               uint32_t v[32];
               tmem_ld32(t_lane + c * 32, v);
               tmem_ld_wait();
@@ -387,16 +596,14 @@ __global__ void __launch_bounds__(NTILES * 128 + 32, 1) rollout_tc_kernel(const 
               for (int q = 0; q < 4; ++q) {
                 const float4 b0 = *reinterpret_cast<const float4*>(bl + c * 32 + q * 8);
                 const float4 b1 = *reinterpret_cast<const float4*>(bl + c * 32 + q * 8 + 4);
-                const uint32_t p0 = pack_relu_bf16(__uint_as_float(v[q * 8 + 0]) + b0.x,
-                                                   __uint_as_float(v[q * 8 + 1]) + b0.y);
-                const uint32_t p1 = pack_relu_bf16(__uint_as_float(v[q * 8 + 2]) + b0.z,
-                                                   __uint_as_float(v[q * 8 + 3]) + b0.w);
-                const uint32_t p2 = pack_relu_bf16(__uint_as_float(v[q * 8 + 4]) + b1.x,
-                                                   __uint_as_float(v[q * 8 + 5]) + b1.y);
-                const uint32_t p3 = pack_relu_bf16(__uint_as_float(v[q * 8 + 6]) + b1.z,
-                                                   __uint_as_float(v[q * 8 + 7]) + b1.w);
+                const float2 f0 = add2(v[q * 8 + 0], v[q * 8 + 1], make_float2(b0.x, b0.y));
+                const float2 f1 = add2(v[q * 8 + 2], v[q * 8 + 3], make_float2(b0.z, b0.w));
+                const float2 f2 = add2(v[q * 8 + 4], v[q * 8 + 5], make_float2(b1.x, b1.y));
+                const float2 f3 = add2(v[q * 8 + 6], v[q * 8 + 7], make_float2(b1.z, b1.w));
                 const uint32_t chunk = (uint32_t)((c & 1) * 4 + q);
-                st_shared_v4(atom + ((chunk ^ swz) << 4), p0, p1, p2, p3);
+                st_shared_v4(atom + ((chunk ^ swz) << 4), pack_relu_bf16(f0.x, f0.y),
+                             pack_relu_bf16(f1.x, f1.y), pack_relu_bf16(f2.x, f2.y),
+                             pack_relu_bf16(f3.x, f3.y));
               }
             }
             tc_fence_before();
@@ -405,66 +612,25 @@ __global__ void __launch_bounds__(NTILES * 128 + 32, 1) rollout_tc_kernel(const 
             if (lane == 0) mbar_arrive(bar_a[j]);
           }
 
-          // ---- Gaussian heads: mu cols [0, 64), raw var cols [64, 128) ----------------------------
+          // ---- Gaussian heads + state update + next input + partial minima (one fused pass) --------
           mbar_wait(bar_acc[j], ph);
           ph ^= 1;
           tc_fence_after();
-          {
-            const float* bh = bias_smem + L * 128;
-#pragma unroll
-            for (int hhalf = 0; hhalf < 2; ++hhalf) {
-              uint32_t vm[32], vv[32];
-              tmem_ld32(t_lane + hhalf * 32, vm);
-              tmem_ld32(t_lane + 64 + hhalf * 32, vv);
-              tmem_ld_wait();
-#pragma unroll
-              for (int jb = 0; jb < 8; ++jb) {
-                const int o0 = hhalf * 32 + jb * 4;
-                if (o0 >= kMaxO) continue;
-                float e4[4] = {0.f, 0.f, 0.f, 0.f};
-                if (prm.sampling_propagation) {
-                  if (prm.eps != nullptr) {
-                    const float* ep = prm.eps + (((int64_t)id.s * H + t) * ((int64_t)g.P * g.N) + id.r_global) * O;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                      if (o0 + q < O) e4[q] = ep[o0 + q];
-                  } else {
-                    const float4 z = philox_normals<true>(seed, kStreamNoise, (uint32_t)id.s,
-                                                          (uint32_t)prm.iteration, (uint32_t)t,
-                                                          (uint32_t)id.r_global, (uint32_t)(o0 >> 2));
-                    e4[0] = z.x; e4[1] = z.y; e4[2] = z.z; e4[3] = z.w;
-                  }
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const int o = o0 + q;
-                  if (o >= kMaxO) continue;
-                  const float mu = __uint_as_float(vm[jb * 4 + q]) + bh[o];
-                  float d = mu;
-                  if (prm.sampling_propagation) {
-                    const float raw = __uint_as_float(vv[jb * 4 + q]) + bh[64 + o];
-                    const float var = softplus_fast(raw) + 1e-4f;
-                    d = fmaf(sqrtf(var), e4[q], mu);
-                  }
-                  if (kPG1 || o < O) s[o] += d;
-                }
-              }
-            }
-          }
-          // the accumulator has been consumed; the next step's first MMA may overwrite it once this
-          // thread's next bar_a arrival (after the A-operand write above) is observed.
+          if (prm.sampling_propagation) state_pass(std::false_type{}, std::true_type{}, t, t + 1);
+          else state_pass(std::false_type{}, std::false_type{}, t, t + 1);
 
           // ---- scoring of (s_t, s_{t+1}): safety_gym.py:110-166, per-row objective ------------------
-          {
-            const float next_dist = goal_dist();
-            const float next_cost = cost_now();
+          named_bar_sync<kTileThreads>(2 + j);
+          if (cgp == 0) {
+            float next_dist, next_cost;
+            combine(next_dist, next_cost);
             const bool goal = rs.dist <= sc.goal_threshold;
             const float rew = step_reward(sc, rs.dist, next_dist, goal);
-            if (done_first) {
+            if (done_first) {                                  // safe_cem_mpc.py:87-93
               rs.done = rs.done || goal;
               if (!rs.done && rs.cost > 0.0f) rs.cmask |= (1ull << t);
               rs.cum += rs.done ? 0.0f : rew;
-            } else {
+            } else {                                           // mpc_policy.py:35-37
               rs.cum += rs.done ? 0.0f : rew;
               if (!rs.done && rs.cost > 0.0f) rs.cmask |= (1ull << t);
               rs.done = rs.done || goal;
@@ -474,7 +640,7 @@ __global__ void __launch_bounds__(NTILES * 128 + 32, 1) rollout_tc_kernel(const 
             rs.cost = next_cost;
           }
         }
-        if (row_ok && prm.row_return != nullptr) {
+        if (cgp == 0 && row_ok && prm.row_return != nullptr) {
           prm.row_return[id.out] = rs.cum;
           prm.row_costmask[id.out] = rs.cmask;
           prm.row_costsum[id.out] = rs.costsum;
@@ -485,7 +651,7 @@ __global__ void __launch_bounds__(NTILES * 128 + 32, 1) rollout_tc_kernel(const 
 
   tc_fence_before();
   __syncthreads();
-  if (is_ctrl) tmem_dealloc(tmem_base, NTILES * 128);
+  if (is_ctrl) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -493,38 +659,36 @@ bool rollout_tc_supported(int O, int A, int L, int U, int H) {
   return U == kU && O >= 1 && O <= kMaxO && O + A <= 64 && L >= 1 && L <= 6 && H >= 1 && H <= 64;
 }
 
-static size_t tc_smem_bytes(int L, int ntiles) {
+static size_t tc_smem_bytes(int L, int ntiles, int q) {
   size_t b = (size_t)kAtomBytes + (size_t)L * 2 * kAtomBytes;      // weights
   b += (size_t)ntiles * 2 * kAtomBytes;                            // A operands
   b += (size_t)(L + 1) * 128 * sizeof(float);                      // biases
+  b += 128 * sizeof(float);                                        // scaler
+  b += kParts * 64 * sizeof(float);                                // slice penalty table
+  b += (size_t)ntiles * q * kParts * 128 * sizeof(float);          // partial minima exchange
   b += (1 + 2 * ntiles) * sizeof(uint64_t) + 2 * sizeof(uint32_t) + ntiles * sizeof(TileInfo);
   return b + 1024;                                                 // alignment slack
 }
 
-template <int NTILES, bool kPG1>
+template <int NTILES, int Q>
 static cudaError_t launch_variant(const RolloutParams& prm, int n_tiles, cudaStream_t stream) {
-  const size_t smem = tc_smem_bytes(prm.L, NTILES);
+  const size_t smem = tc_smem_bytes(prm.L, NTILES, Q);
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(rollout_tc_kernel<NTILES, kPG1>,
+    cudaError_t e = cudaFuncSetAttribute(rollout_tc_kernel<NTILES, Q>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
   const int grid = (n_tiles + NTILES - 1) / NTILES;
-  rollout_tc_kernel<NTILES, kPG1><<<grid, NTILES * 128 + 32, smem, stream>>>(prm);
+  rollout_tc_kernel<NTILES, Q><<<grid, NTILES * Q * 128 + 32, smem, stream>>>(prm);
   return cudaGetLastError();
 }
 
 cudaError_t launch_rollout_tc(const RolloutParams& prm, int n_tiles, cudaStream_t stream) {
   if (n_tiles == 0) return cudaSuccess;
-  const simba_scorer_t& sc = prm.scorer;
-  const bool pg1 = prm.g.O == 60 && prm.g.A == 2 && sc.goal_dist_index < 0 && sc.goal_begin == 3 &&
-                   sc.goal_end == 19 && sc.n_constraints == 1 && sc.con_begin[0] == 22 &&
-                   sc.con_end[0] == 38;
-  const bool two = prm.tc_tiles_per_cta == 2;
-  if (pg1) return two ? launch_variant<2, true>(prm, n_tiles, stream) : launch_variant<1, true>(prm, n_tiles, stream);
-  return two ? launch_variant<2, false>(prm, n_tiles, stream) : launch_variant<1, false>(prm, n_tiles, stream);
+  if (prm.tc_tiles_per_cta == 2) return launch_variant<2, 2>(prm, n_tiles, stream);
+  return launch_variant<1, 4>(prm, n_tiles, stream);
 }
 
 }  // namespace simba
