@@ -360,14 +360,8 @@ def bench_c3(synthetic, torch, dist, lib, _lib, precision, world, rank):
                                  rank=rank, world_size=world)
     pol.build()
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            buf = (C.c_char * 128)()
-            _lib.check(lib.simba_nccl_unique_id(buf))
-            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
-        uid = uid.cuda()
-        dist.broadcast(uid, 0)
-        pol.init_distributed(bytes(uid.cpu().numpy().tobytes()))
+        from simba_b200 import distributed as sd
+        sd.init_population_sharding(pol)
     st = torch.from_numpy(synthetic.make_state(c['sensors'], seed=400, n_states=1).reshape(1, -1)).cuda()
     pol.plan_device(st, seed=5)
     torch.cuda.synchronize()
