@@ -142,7 +142,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
-    ap.add_argument('--extras', default='', help="comma list of: c3, c4, fp32")
+    ap.add_argument('--extras', default=None, help="comma list of: c3, c4, fp32 (default: c3 when N > 1, c4 when N == 1)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -292,13 +292,18 @@ def main():
 
     # ---- extras -----------------------------------------------------------------------------------
     extras = {}
+    if args.extras is None:
+        args.extras = 'c3' if world > 1 else 'c4'
     want = [x for x in args.extras.split(',') if x]
-    if 'fp32' in want and precision != 'fp32':
-        extras['fp32'] = bench_plain(synthetic, torch, c, 'fp32', states, flush, min(K, 50))
-    if 'c4' in want:
-        extras['c4'] = bench_batched(synthetic, torch, precision, flush, world, rank)
-    if 'c3' in want:
-        extras['c3'] = bench_c3(synthetic, torch, dist, lib, _lib, precision, world, rank)
+    try:
+        if 'fp32' in want and precision != 'fp32':
+            extras['fp32'] = bench_plain(synthetic, torch, c, 'fp32', states, flush, min(K, 50))
+        if 'c4' in want:
+            extras['c4'] = bench_batched(synthetic, torch, precision, flush, world, rank)
+        if 'c3' in want:
+            extras['c3'] = bench_c3(synthetic, torch, dist, lib, _lib, precision, world, rank)
+    except Exception as e:                      # extras never take the headline line down
+        extras['error'] = repr(e)
     if extras:
         line['extras'] = extras
 
