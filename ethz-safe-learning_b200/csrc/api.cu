@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -436,6 +437,7 @@ struct simba_planner {
   Tile* d_tiles = nullptr;
   int tile_rows = 0;
   int tiles_per_cta = 1;
+  bool fused_update = false;   // one rank, N <= 1024: reduce+select+refit(+next sample | finalize) in one kernel
   int c_max = -1;
   // workspace
   float *actions = nullptr, *row_ret = nullptr, *row_csum = nullptr, *pairs_local = nullptr,
@@ -570,6 +572,7 @@ extern "C" int simba_planner_create(simba_model_t* model, const simba_planner_co
     p->tiles_per_cta = 2;
     build_tiles(p->geom, p->tile_rows, p->tiles, 2);
   }
+  p->fused_update = cfg->world_size == 1 && cfg->n_samples <= 1024 && getenv("SIMBA_B200_NO_FUSE") == nullptr;
   p->c_max = beta_count_threshold(cfg->particles, cfg->posterior_mean_threshold, cfg->prior_mu,
                                   cfg->prior_sigma);
 
@@ -670,10 +673,9 @@ extern "C" int simba_planner_copy_buffer(simba_planner_t* p, int32_t which, void
 }
 
 // ---- per-kernel entry points -------------------------------------------------------------------
-static int do_sample_actions(simba_planner_t* p, const float* mu, const float* sigma,
-                             const float* z, uint64_t seed, const uint64_t* seed_ptr,
-                             int32_t iteration, const int32_t* active, float* out, void* stream) {
-  if (!p || !mu || !sigma || !out) return fail(SIMBA_ERR_BAD_CONFIG, "null argument");
+static SampleParams make_sample_params(simba_planner_t* p, const float* mu, const float* sigma,
+                                       const float* z, uint64_t seed, const uint64_t* seed_ptr,
+                                       int32_t iteration, const int32_t* active, float* out) {
   SampleParams sp{};
   sp.seed_ptr = seed_ptr;
   sp.S = p->cfg.n_states; sp.N = p->cfg.n_samples; sp.H = p->cfg.horizon; sp.A = p->model->cfg.act_dim;
@@ -681,6 +683,14 @@ static int do_sample_actions(simba_planner_t* p, const float* mu, const float* s
   sp.active = active; sp.out = out;
   memcpy(sp.lb, p->cfg.act_low, sizeof(sp.lb));
   memcpy(sp.ub, p->cfg.act_high, sizeof(sp.ub));
+  return sp;
+}
+
+static int do_sample_actions(simba_planner_t* p, const float* mu, const float* sigma,
+                             const float* z, uint64_t seed, const uint64_t* seed_ptr,
+                             int32_t iteration, const int32_t* active, float* out, void* stream) {
+  if (!p || !mu || !sigma || !out) return fail(SIMBA_ERR_BAD_CONFIG, "null argument");
+  const SampleParams sp = make_sample_params(p, mu, sigma, z, seed, seed_ptr, iteration, active, out);
   CUDA_TRY(launch_sample_actions(sp, (cudaStream_t)stream));
   return SIMBA_OK;
 }
@@ -727,16 +737,57 @@ extern "C" int simba_rollout_score(simba_planner_t* p, const float* states, cons
                           row_costmask, row_costsum, stream);
 }
 
-extern "C" int simba_score_reduce(simba_planner_t* p, const float* row_return,
-                                  const uint64_t* row_costmask, const float* row_costsum,
-                                  const int32_t* active, float* out_pairs_local, void* stream) {
-  if (!p || !row_return || !row_costmask || !row_costsum || !out_pairs_local)
-    return fail(SIMBA_ERR_BAD_CONFIG, "null argument");
+static ReduceParams make_reduce_params(simba_planner_t* p, const float* row_return,
+                                       const uint64_t* row_costmask, const float* row_costsum,
+                                       const int32_t* active, float* out_pairs_local) {
   ReduceParams rp{};
   rp.S = p->cfg.n_states; rp.P = p->cfg.particles; rp.N_local = p->geom.N_local;
   rp.H = p->cfg.horizon; rp.objective = p->cfg.objective;
   rp.row_return = row_return; rp.row_costmask = row_costmask; rp.row_costsum = row_costsum;
   rp.active = active; rp.out_pairs = out_pairs_local;
+  return rp;
+}
+
+static SelectParams make_select_params(simba_planner_t* p, const float* pairs_all, const float* actions,
+                                       const int32_t* active, int32_t* out_elite, float* out_scores,
+                                       float* best_action, float* best_score) {
+  SelectParams sp{};
+  sp.S = p->cfg.n_states; sp.N = p->cfg.n_samples; sp.N_local = p->geom.N_local;
+  sp.K = p->cfg.n_elite; sp.H = p->cfg.horizon; sp.A = p->model->cfg.act_dim;
+  sp.objective = p->cfg.objective; sp.c_max = (float)p->c_max;
+  sp.pairs_all = pairs_all; sp.actions = actions; sp.active = active; sp.out_elite = out_elite;
+  sp.out_scores = out_scores; sp.best_action = best_action; sp.best_score = best_score;
+  return sp;
+}
+
+static RefitParams make_refit_params(simba_planner_t* p, const float* actions, const int32_t* elite,
+                                     float* mu, float* sigma, int32_t* active, int32_t* iterations_run) {
+  RefitParams rp{};
+  rp.S = p->cfg.n_states; rp.N = p->cfg.n_samples; rp.K = p->cfg.n_elite; rp.H = p->cfg.horizon;
+  rp.A = p->model->cfg.act_dim;
+  rp.smoothing = p->cfg.smoothing;
+  rp.one_minus_smoothing = (float)(1.0 - (double)p->cfg.smoothing);
+  rp.stddev_threshold = p->cfg.stddev_threshold;
+  rp.actions = actions; rp.elite = elite; rp.mu = mu; rp.sigma = sigma; rp.active = active;
+  rp.iterations_run = iterations_run;
+  return rp;
+}
+
+static FinalizeParams make_finalize_params(simba_planner_t* p, const float* best_action, const float* z,
+                                           uint64_t seed, const uint64_t* seed_ptr, float* out_action) {
+  FinalizeParams fp{};
+  fp.seed_ptr = seed_ptr;
+  fp.S = p->cfg.n_states; fp.A = p->model->cfg.act_dim; fp.noise_stddev = p->cfg.noise_stddev;
+  fp.best = best_action; fp.z = z; fp.seed = seed; fp.out = out_action;
+  return fp;
+}
+
+extern "C" int simba_score_reduce(simba_planner_t* p, const float* row_return,
+                                  const uint64_t* row_costmask, const float* row_costsum,
+                                  const int32_t* active, float* out_pairs_local, void* stream) {
+  if (!p || !row_return || !row_costmask || !row_costsum || !out_pairs_local)
+    return fail(SIMBA_ERR_BAD_CONFIG, "null argument");
+  const ReduceParams rp = make_reduce_params(p, row_return, row_costmask, row_costsum, active, out_pairs_local);
   CUDA_TRY(launch_score_reduce(rp, (cudaStream_t)stream));
   return SIMBA_OK;
 }
@@ -762,12 +813,8 @@ extern "C" int simba_select_elites(simba_planner_t* p, const float* pairs_all, c
                                    float* best_action, float* best_score, void* stream) {
   if (!p || !pairs_all || !actions || !out_elite || !best_action || !best_score)
     return fail(SIMBA_ERR_BAD_CONFIG, "null argument");
-  SelectParams sp{};
-  sp.S = p->cfg.n_states; sp.N = p->cfg.n_samples; sp.N_local = p->geom.N_local;
-  sp.K = p->cfg.n_elite; sp.H = p->cfg.horizon; sp.A = p->model->cfg.act_dim;
-  sp.objective = p->cfg.objective; sp.c_max = (float)p->c_max;
-  sp.pairs_all = pairs_all; sp.actions = actions; sp.active = active; sp.out_elite = out_elite;
-  sp.out_scores = out_scores; sp.best_action = best_action; sp.best_score = best_score;
+  const SelectParams sp = make_select_params(p, pairs_all, actions, active, out_elite, out_scores,
+                                             best_action, best_score);
   CUDA_TRY(launch_select_elites(sp, (cudaStream_t)stream));
   return SIMBA_OK;
 }
@@ -775,14 +822,7 @@ extern "C" int simba_select_elites(simba_planner_t* p, const float* pairs_all, c
 extern "C" int simba_refit(simba_planner_t* p, const float* actions, const int32_t* elite, float* mu,
                            float* sigma, int32_t* active, int32_t* iterations_run, void* stream) {
   if (!p || !actions || !elite || !mu || !sigma) return fail(SIMBA_ERR_BAD_CONFIG, "null argument");
-  RefitParams rp{};
-  rp.S = p->cfg.n_states; rp.N = p->cfg.n_samples; rp.K = p->cfg.n_elite; rp.H = p->cfg.horizon;
-  rp.A = p->model->cfg.act_dim;
-  rp.smoothing = p->cfg.smoothing;
-  rp.one_minus_smoothing = (float)(1.0 - (double)p->cfg.smoothing);
-  rp.stddev_threshold = p->cfg.stddev_threshold;
-  rp.actions = actions; rp.elite = elite; rp.mu = mu; rp.sigma = sigma; rp.active = active;
-  rp.iterations_run = iterations_run;
+  const RefitParams rp = make_refit_params(p, actions, elite, mu, sigma, active, iterations_run);
   CUDA_TRY(launch_refit(rp, (cudaStream_t)stream));
   return SIMBA_OK;
 }
@@ -791,10 +831,7 @@ static int do_finalize_action(simba_planner_t* p, const float* best_action, cons
                               uint64_t seed, const uint64_t* seed_ptr, float* out_action,
                               void* stream) {
   if (!p || !best_action || !out_action) return fail(SIMBA_ERR_BAD_CONFIG, "null argument");
-  FinalizeParams fp{};
-  fp.seed_ptr = seed_ptr;
-  fp.S = p->cfg.n_states; fp.A = p->model->cfg.act_dim; fp.noise_stddev = p->cfg.noise_stddev;
-  fp.best = best_action; fp.z = z; fp.seed = seed; fp.out = out_action;
+  const FinalizeParams fp = make_finalize_params(p, best_action, z, seed, seed_ptr, out_action);
   CUDA_TRY(launch_finalize(fp, (cudaStream_t)stream));
   return SIMBA_OK;
 }
@@ -825,6 +862,33 @@ static int enqueue_plan(simba_planner* p, cudaStream_t st, int* n_launches) {
   CUDA_TRY(launch_plan_init(ip, st)); ++launches;
   const bool multi = c.world_size > 1;
   float* pairs_all = multi ? p->pairs_all : p->pairs_local;
+  if (p->fused_update) {
+    // small population on one rank: sample(0), then per iteration rollout + one fused update kernel
+    const float* z0 = p->ext_z_actions;
+    int rc = do_sample_actions(p, p->mu, p->sigma, z0, 0, sp, 0, p->active, p->actions, st);
+    if (rc) return rc; ++launches;
+    for (int it = 0; it < c.iterations; ++it) {
+      const float* eps = p->ext_eps ? p->ext_eps + (size_t)it * S * c.horizon * B * O : nullptr;
+      rc = do_rollout_score(p, p->d_states, p->actions, eps, 0, sp, it, p->active, p->row_ret,
+                            p->row_cmask, p->row_csum, st);
+      if (rc) return rc; ++launches;
+      UpdateParams u{};
+      u.reduce = make_reduce_params(p, p->row_ret, p->row_cmask, p->row_csum, p->active, p->pairs_local);
+      u.select = make_select_params(p, p->pairs_local, p->actions, p->active, p->elite, nullptr,
+                                    p->best_action, p->best_score);
+      u.refit = make_refit_params(p, p->actions, p->elite, p->mu, p->sigma, p->active, p->iters);
+      const float* zn = (p->ext_z_actions && it + 1 < c.iterations)
+                            ? p->ext_z_actions + (size_t)(it + 1) * S * N * HA : nullptr;
+      u.sample = make_sample_params(p, p->mu, p->sigma, zn, 0, sp, it + 1, p->active, p->actions);
+      u.finalize = make_finalize_params(p, p->best_action, p->ext_z_final, 0, sp, p->d_out_action);
+      u.last = (it + 1 == c.iterations) ? 1 : 0;
+      u.out_score = p->d_out_score;
+      u.out_iters = p->d_out_iters;
+      CUDA_TRY(launch_cem_update(u, st)); ++launches;
+    }
+    if (n_launches) *n_launches = launches;
+    return SIMBA_OK;
+  }
   for (int it = 0; it < c.iterations; ++it) {
     const float* z = p->ext_z_actions ? p->ext_z_actions + (size_t)it * S * N * HA : nullptr;
     const float* eps = p->ext_eps ? p->ext_eps + (size_t)it * S * c.horizon * B * O : nullptr;
@@ -880,7 +944,7 @@ static int upload_seed(simba_planner* p, uint64_t seed, cudaStream_t st) {
 extern "C" int simba_planner_launches_per_plan(simba_planner_t* p, int32_t* out) {
   if (!p || !out) return fail(SIMBA_ERR_BAD_CONFIG, "null argument");
   const int per_iter = 5 + (p->cfg.world_size > 1 ? 1 : 0);
-  *out = 1 + per_iter * p->cfg.iterations + 2;
+  *out = p->fused_update ? 2 + 2 * p->cfg.iterations : 1 + per_iter * p->cfg.iterations + 2;
   return SIMBA_OK;
 }
 

@@ -11,9 +11,41 @@ namespace simba {
 //     a = clip_by_value(z * sigma + mu, lb, ub);  z external or Philox stream ACTION.
 // One thread = 4 consecutive flattened (h, a) elements of one candidate (= one Philox block).
 // =============================================================================================
-__global__ void __launch_bounds__(256) sample_actions_kernel(SampleParams p) {
+// one Philox block = 4 consecutive flattened (h, a) elements of candidate i of state s
+__device__ __forceinline__ void sample_block(const SampleParams& p, int s, int i, int j) {
   const int HA = p.H * p.A;
-  const int JB = (HA + 3) >> 2;
+  const long base = ((long)s * p.N + i) * HA + 4 * j;
+  float z[4];
+  if (p.z != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) z[q] = (4 * j + q < HA) ? p.z[base + q] : 0.0f;
+  } else {
+    const float4 n = philox_normals<false>(p.seed_ptr ? *p.seed_ptr : p.seed, kStreamAction,
+                                           (uint32_t)s, (uint32_t)p.iteration, 0u, (uint32_t)i, (uint32_t)j);
+    z[0] = n.x; z[1] = n.y; z[2] = n.z; z[3] = n.w;
+  }
+  float out[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int e = 4 * j + q;
+    out[q] = 0.0f;
+    if (e < HA) {
+      const int a = e % p.A;
+      const float v = __fadd_rn(__fmul_rn(z[q], p.sigma[s * HA + e]), p.mu[s * HA + e]);
+      out[q] = fminf(fmaxf(v, p.lb[a]), p.ub[a]);
+    }
+  }
+  if ((HA & 3) == 0) {
+    *reinterpret_cast<float4*>(p.out + base) = make_float4(out[0], out[1], out[2], out[3]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (4 * j + q < HA) p.out[base + q] = out[q];
+  }
+}
+
+__global__ void __launch_bounds__(256) sample_actions_kernel(SampleParams p) {
+  const int JB = (p.H * p.A + 3) >> 2;
   const long total = (long)p.S * p.N * JB;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
        idx += (long)gridDim.x * blockDim.x) {
@@ -22,33 +54,7 @@ __global__ void __launch_bounds__(256) sample_actions_kernel(SampleParams p) {
     const int s = (int)(si / p.N);
     const int i = (int)(si - (long)s * p.N);
     if (p.active != nullptr && p.active[s] == 0) continue;
-    const long base = si * HA + 4 * j;
-    float z[4];
-    if (p.z != nullptr) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) z[q] = (4 * j + q < HA) ? p.z[base + q] : 0.0f;
-    } else {
-      const float4 n = philox_normals<false>(p.seed_ptr ? *p.seed_ptr : p.seed, kStreamAction, (uint32_t)s,
-                                             (uint32_t)p.iteration, 0u, (uint32_t)i, (uint32_t)j);
-      z[0] = n.x; z[1] = n.y; z[2] = n.z; z[3] = n.w;
-    }
-    float out[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int e = 4 * j + q;
-      if (e < HA) {
-        const int a = e % p.A;
-        const float v = __fadd_rn(__fmul_rn(z[q], p.sigma[s * HA + e]), p.mu[s * HA + e]);
-        out[q] = fminf(fmaxf(v, p.lb[a]), p.ub[a]);
-      }
-    }
-    if ((HA & 3) == 0) {
-      *reinterpret_cast<float4*>(p.out + base) = make_float4(out[0], out[1], out[2], out[3]);
-    } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (4 * j + q < HA) p.out[base + q] = out[q];
-    }
+    sample_block(p, s, i, j);
   }
 }
 
@@ -71,17 +77,12 @@ cudaError_t launch_sample_actions(const SampleParams& p, cudaStream_t st) {
 // the H x P popcount costs ~3 logic ops per particle and plane. Summation order over particles
 // is fixed (p ascending) => bit-identical on every rank.
 // =============================================================================================
-__global__ void __launch_bounds__(256) score_reduce_kernel(ReduceParams p) {
-  const long total = (long)p.S * p.N_local;
-  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int s = (int)(idx / p.N_local);
-  const int i = (int)(idx - (long)s * p.N_local);
-  if (p.active != nullptr && p.active[s] == 0) return;
+__device__ __forceinline__ float2 reduce_candidate(const ReduceParams& p, int s, int i) {
   float ret = 0.0f, csum = 0.0f;
   uint64_t plane[8];
 #pragma unroll
   for (int b = 0; b < 8; ++b) plane[b] = 0ull;
+#pragma unroll 4
   for (int q = 0; q < p.P; ++q) {
     const long r = ((long)s * p.P + q) * p.N_local + i;
     ret = __fadd_rn(ret, p.row_return[r]);
@@ -108,7 +109,17 @@ __global__ void __launch_bounds__(256) score_reduce_kernel(ReduceParams p) {
     }
     cost = (float)maxc;
   }
-  reinterpret_cast<float2*>(p.out_pairs)[idx] = make_float2(mean_ret, cost);
+  return make_float2(mean_ret, cost);
+}
+
+__global__ void __launch_bounds__(256) score_reduce_kernel(ReduceParams p) {
+  const long total = (long)p.S * p.N_local;
+  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int s = (int)(idx / p.N_local);
+  const int i = (int)(idx - (long)s * p.N_local);
+  if (p.active != nullptr && p.active[s] == 0) return;
+  reinterpret_cast<float2*>(p.out_pairs)[idx] = reduce_candidate(p, s, i);
 }
 
 cudaError_t launch_score_reduce(const ReduceParams& p, cudaStream_t st) {
@@ -287,17 +298,15 @@ cudaError_t launch_select_elites(const SelectParams& p, cudaStream_t st) {
 // =============================================================================================
 constexpr int kRefitThreads = 1024;
 
-__global__ void __launch_bounds__(kRefitThreads) refit_kernel(RefitParams p) {
-  const int s = blockIdx.x;
-  if (p.active != nullptr && p.active[s] == 0) return;
-  extern __shared__ float sh[];           // [groups][HA] partials, then [HA] mean, [HA] sigma
+// `elite` may live in global or shared memory; `sh` needs (groups + 2) * HA floats.
+// Must be called by all kRefitThreads threads of the CTA.
+__device__ __forceinline__ void refit_body(const RefitParams& p, int s, const int* elite, float* sh) {
   const int HA = p.H * p.A;
   const int groups = kRefitThreads / HA > 0 ? kRefitThreads / HA : 1;
   float* part = sh;
   float* mean = part + groups * HA;
   float* sig = mean + HA;
   const int tid = threadIdx.x;
-  const int* elite = p.elite + (long)s * p.K;
   const float* acts = p.actions + (long)s * p.N * HA;
   const float kf = (float)p.K;
 
@@ -315,31 +324,37 @@ __global__ void __launch_bounds__(kRefitThreads) refit_kernel(RefitParams p) {
     }
     __syncthreads();
     for (int cc = tid; cc < HA; cc += kRefitThreads) {
-      const int c = cc;
       float tot = 0.0f;
-      for (int gI = 0; gI < groups; ++gI) tot = __fadd_rn(tot, part[gI * HA + c]);
+      for (int gI = 0; gI < groups; ++gI) tot = __fadd_rn(tot, part[gI * HA + cc]);
       const float r = __fdiv_rn(tot, kf);
-      if (pass == 0) mean[c] = r;
+      if (pass == 0) mean[cc] = r;
       else {
         const float sd = sqrtf(r);                                        // cem_mpc.py:63
-        const float mu_new = __fadd_rn(__fmul_rn(p.smoothing, p.mu[s * HA + c]),
-                                       __fmul_rn(p.one_minus_smoothing, mean[c]));
-        const float sg_new = __fadd_rn(__fmul_rn(p.smoothing, p.sigma[s * HA + c]),
+        const float mu_new = __fadd_rn(__fmul_rn(p.smoothing, p.mu[s * HA + cc]),
+                                       __fmul_rn(p.one_minus_smoothing, mean[cc]));
+        const float sg_new = __fadd_rn(__fmul_rn(p.smoothing, p.sigma[s * HA + cc]),
                                        __fmul_rn(p.one_minus_smoothing, sd));
-        p.mu[s * HA + c] = mu_new;                                        // cem_mpc.py:64-65
-        p.sigma[s * HA + c] = sg_new;
-        sig[c] = sg_new;
+        p.mu[s * HA + cc] = mu_new;                                       // cem_mpc.py:64-65
+        p.sigma[s * HA + cc] = sg_new;
+        sig[cc] = sg_new;
       }
     }
     __syncthreads();
   }
   if (tid == 0) {
     float tot = 0.0f;
-    for (int c = 0; c < HA; ++c) tot = __fadd_rn(tot, sig[c]);
+    for (int cc = 0; cc < HA; ++cc) tot = __fadd_rn(tot, sig[cc]);
     if (p.iterations_run != nullptr) p.iterations_run[s] += 1;
     if (p.active != nullptr && __fdiv_rn(tot, (float)HA) <= p.stddev_threshold)  // cem_mpc.py:66-67
       p.active[s] = 0;
   }
+}
+
+__global__ void __launch_bounds__(kRefitThreads) refit_kernel(RefitParams p) {
+  const int s = blockIdx.x;
+  if (p.active != nullptr && p.active[s] == 0) return;
+  extern __shared__ float sh[];           // [groups][HA] partials, then [HA] mean, [HA] sigma
+  refit_body(p, s, p.elite + (long)s * p.K, sh);
 }
 
 cudaError_t launch_refit(const RefitParams& p, cudaStream_t st) {
@@ -353,9 +368,7 @@ cudaError_t launch_refit(const RefitParams& p, cudaStream_t st) {
 // =============================================================================================
 // k11  final noise — simba/policies/cem_mpc.py:68 : best + z * noise_stddev (not re-clipped)
 // =============================================================================================
-__global__ void finalize_kernel(FinalizeParams p) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p.S * p.A) return;
+__device__ __forceinline__ void finalize_element(const FinalizeParams& p, int idx) {
   const int s = idx / p.A, a = idx - s * p.A;
   float z;
   if (p.z != nullptr) z = p.z[idx];
@@ -368,9 +381,103 @@ __global__ void finalize_kernel(FinalizeParams p) {
   p.out[idx] = __fadd_rn(p.best[idx], __fadd_rn(__fmul_rn(z, p.noise_stddev), 0.0f));
 }
 
+__global__ void finalize_kernel(FinalizeParams p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.S * p.A) return;
+  finalize_element(p, idx);
+}
+
 cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t st) {
   const int n = p.S * p.A;
   finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// Fused CEM update for small populations (one rank, N <= 1024): k8 + k9 + k10 of this iteration,
+// then k1 of the NEXT iteration (or k11 + the plan outputs after the last one), one CTA per state.
+// Same device functions and the same arithmetic order as the separate kernels (bit-identical
+// results); what it removes is 3-4 kernel boundaries per iteration on the latency-bound C1 plan.
+// Selection is rank-by-counting: thread i owns candidate i and counts the keys that beat it.
+// =============================================================================================
+__global__ void __launch_bounds__(kRefitThreads) cem_update_kernel(UpdateParams u) {
+  const int s = blockIdx.x;
+  const int tid = threadIdx.x;
+  extern __shared__ float sh[];                       // refit scratch, then keys / elite list
+  const int HA = u.refit.H * u.refit.A;
+  const int groups = kRefitThreads / HA > 0 ? kRefitThreads / HA : 1;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(sh + (groups + 2) * HA + ((groups + 2) * HA & 1));
+  int* elite_sh = reinterpret_cast<int*>(keys + u.select.N);
+  __shared__ int warp_sums[32];
+  __shared__ int sh_total;
+  const int N = u.select.N, K = u.select.K;
+  const bool active = u.refit.active == nullptr || u.refit.active[s] != 0;
+  __syncthreads();                                    // everyone has read active[s] before refit clears it
+
+  if (active) {
+    // ---- k8: (return, cost) of candidate tid --------------------------------------------------
+    float2 pr = make_float2(0.0f, 0.0f);
+    unsigned long long key = 0ull;
+    if (tid < N) {
+      pr = reduce_candidate(u.reduce, s, tid);
+      if (u.reduce.out_pairs != nullptr) reinterpret_cast<float2*>(u.reduce.out_pairs)[(long)s * N + tid] = pr;
+      key = pair_key(u.select.objective, pr.x, pr.y, u.select.c_max);
+      keys[tid] = key;
+    }
+    __syncthreads();
+    // ---- k9: rank by counting (ties -> lower index), ordered compaction, best-so-far ------------
+    int rank = 0;
+    if (tid < N)
+      for (int jn = 0; jn < N; ++jn) {
+        const unsigned long long kj = keys[jn];
+        rank += (kj > key || (kj == key && jn < tid)) ? 1 : 0;
+      }
+    const int sel = (tid < N && rank < K) ? 1 : 0;
+    const int pos = block_exclusive_scan<kRefitThreads>(sel, warp_sums, &sh_total);
+    if (sel) {
+      elite_sh[pos] = tid;
+      u.select.out_elite[(long)s * K + pos] = tid;
+    }
+    if (tid < N && u.select.out_scores != nullptr)
+      u.select.out_scores[(long)s * N + tid] = pair_score(u.select.objective, pr.x, pr.y, u.select.c_max);
+    if (tid < N && rank == 0) {                                   // argmax, first max
+      const float top_score = pair_score(u.select.objective, pr.x, pr.y, u.select.c_max);
+      if (top_score > u.select.best_score[s]) {                   // cem_mpc.py:58 strict '>'
+        for (int a = 0; a < u.select.A; ++a)
+          u.select.best_action[s * u.select.A + a] = u.select.actions[((long)s * N + tid) * HA + a];
+        u.select.best_score[s] = top_score;
+      }
+    }
+    __syncthreads();
+    // ---- k10: refit (also clears active[s] when the stddev threshold is met) --------------------
+    refit_body(u.refit, s, elite_sh, sh);
+    __syncthreads();
+  }
+  if (!u.last) {
+    // ---- k1 of the next iteration (skipped for states that just stopped, like the early break) --
+    const bool still = u.refit.active == nullptr || u.refit.active[s] != 0;
+    if (active && still) {
+      const int JB = (HA + 3) >> 2;
+      for (int idx = tid; idx < N * JB; idx += kRefitThreads) sample_block(u.sample, s, idx / JB, idx % JB);
+    }
+  } else {
+    // ---- k11 + plan outputs ----------------------------------------------------------------------
+    __threadfence_block();
+    __syncthreads();
+    if (tid < u.finalize.A) finalize_element(u.finalize, s * u.finalize.A + tid);
+    if (tid == 0) {
+      u.out_score[s] = u.select.best_score[s];
+      if (u.out_iters != nullptr) u.out_iters[s] = u.refit.iterations_run[s];
+    }
+  }
+}
+
+cudaError_t launch_cem_update(const UpdateParams& u, cudaStream_t st) {
+  const int HA = u.refit.H * u.refit.A;
+  const int groups = kRefitThreads / HA > 0 ? kRefitThreads / HA : 1;
+  size_t smem = (size_t)((groups + 2) * HA + 1) * sizeof(float);
+  smem = (smem + 7) / 8 * 8 + (size_t)u.select.N * 8 + (size_t)u.select.K * 4 + 16;
+  cem_update_kernel<<<u.refit.S, kRefitThreads, smem, st>>>(u);
   return cudaGetLastError();
 }
 

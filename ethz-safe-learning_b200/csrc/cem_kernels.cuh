@@ -70,6 +70,18 @@ struct PlanInitParams {               // cem_mpc.py:36-42
   int32_t* iterations_run;
 };
 
+struct UpdateParams {                 // fused k8 + k9 + k10 (+ next k1 | k11): one rank, N <= 1024
+  ReduceParams reduce;
+  SelectParams select;
+  RefitParams refit;
+  SampleParams sample;                // next iteration's sampling (ignored when last)
+  FinalizeParams finalize;            // used when last
+  int32_t last;
+  float* out_score;
+  int32_t* out_iters;
+};
+
+cudaError_t launch_cem_update(const UpdateParams& u, cudaStream_t st);
 cudaError_t launch_sample_actions(const SampleParams& p, cudaStream_t st);
 cudaError_t launch_score_reduce(const ReduceParams& p, cudaStream_t st);
 cudaError_t launch_select_elites(const SelectParams& p, cudaStream_t st);

@@ -143,3 +143,29 @@ def test_policy_reconstruction_shares_weights():
     b = pol2.do_generate_action(c['state'], seed=3)[0]
     assert pol2.model.model._handle is pol.model.model._handle
     assert a.shape == b.shape == (c['A'],) and np.all(np.isfinite(b))
+
+
+@pytest.mark.parametrize("precision", ['fp32', 'bf16'])
+def test_fused_update_kernel_is_bit_identical_to_separate_kernels(precision):
+    """One rank, N <= 1024: reduce + select + refit (+ next sampling | finalize) run as one kernel.
+    It must reproduce the separate k8 / k9 / k10 / k1 / k11 kernels bit for bit."""
+    import os
+    from simba_b200 import _lib
+    c = helpers.workload('c1')
+    res = []
+    for no_fuse in (False, True):
+        if no_fuse:
+            os.environ['SIMBA_B200_NO_FUSE'] = '1'
+        try:
+            pol = helpers.cuda_policy(c, 'penalty', precision=precision, stddev_threshold=0.45)
+            a, s = pol.do_generate_action(c['state'], seed=123)
+            res.append((a, s, pol.buffer(_lib.BUF_MU).cpu().numpy(), pol.buffer(_lib.BUF_SIGMA).cpu().numpy(),
+                        pol.buffer(_lib.BUF_ELITE, torch.int32).cpu().numpy(), int(pol.iterations_run[0]),
+                        pol.launches_per_plan))
+        finally:
+            os.environ.pop('SIMBA_B200_NO_FUSE', None)
+    f, u = res
+    assert f[6] < u[6]                                   # fewer launches
+    assert np.array_equal(f[0], u[0]) and f[1] == u[1]
+    assert np.array_equal(f[2], u[2]) and np.array_equal(f[3], u[3]) and np.array_equal(f[4], u[4])
+    assert f[5] == u[5] and 1 <= f[5] <= c['I']
