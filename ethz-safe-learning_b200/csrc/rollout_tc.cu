@@ -13,9 +13,12 @@
 //     each reads its column slice of the fp32 accumulator row from TMEM (tcgen05.ld 32x32b), applies
 //     bias + ReLU, packs bf16 and stores straight into the 128B-swizzled K-major A tile of the next
 //     layer; the thread count per SM sub-partition (4 warps) is what hides the MUFU / TMEM latencies;
-//   * one elected thread issues tcgen05.mma (M=128, N=128, K=16 per instruction, fp32 accumulate in
-//     TMEM) and tcgen05.commit; two mbarriers per tile (A ready / accumulator ready) are the only
-//     CTA-level synchronisation, so with two tiles the MMAs of one overlap the epilogue of the other;
+//   * per tile and layer: the tile's threads write the A tile, fence it to the async proxy and meet
+//     at a named barrier (bar.sync, tile threads only); one elected thread of the tile then issues
+//     tcgen05.mma (M=128, N=128, K=16 per instruction, fp32 accumulate in TMEM) and tcgen05.commit
+//     onto the tile's "accumulator ready" mbarrier, on which all threads of the tile wait. There is
+//     no separate MMA warp to wake up; with two tiles per CTA the tensor pipe works on one tile
+//     while the other tile's threads run their epilogue;
 //   * the rollout state s_t (fp32) lives in spare TMEM columns next to the accumulators, so it costs
 //     no registers between steps. The Gaussian-head epilogue is ONE pass over 16-wide column chunks:
 //     load mu / raw-var accumulators and the state chunk from TMEM, softplus, sqrt, Philox4x32-10 +
@@ -229,7 +232,7 @@ struct TileInfo {
 
 // NTILES row tiles per CTA, Q epilogue threads per rollout row.
 template <int NTILES, int Q>
-__global__ void __launch_bounds__(NTILES* Q * 128 + 32, 1) rollout_tc_kernel(const RolloutParams prm) {
+__global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const RolloutParams prm) {
   constexpr int kTileThreads = Q * 128;
   constexpr int kEpiThreads = NTILES * kTileThreads;
   constexpr int OW = 64 / Q;          // head outputs (= state dims = layer-0 K elements) per thread
@@ -242,8 +245,6 @@ __global__ void __launch_bounds__(NTILES* Q * 128 + 32, 1) rollout_tc_kernel(con
   const int H = g.H;
   const int O = g.O, A = g.A;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kCtrlWarp = NTILES * Q * 4;
-  const bool is_ctrl = warp == kCtrlWarp;
 
   // ---- shared memory carve-up (base is 1024-aligned: required by SWIZZLE_128B) -------------------
   const uint32_t w_bytes = kAtomBytes + (uint32_t)L * 2 * kAtomBytes;     // layer 0: 1 atom; others: 2
@@ -254,25 +255,19 @@ __global__ void __launch_bounds__(NTILES* Q * 128 + 32, 1) rollout_tc_kernel(con
   float* pen_smem = scale_smem + 128;                                      // [kParts][64]: 0 in slice, +inf outside
   float* part_smem = pen_smem + kParts * 64;                               // [NTILES][Q][kParts][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(part_smem + NTILES * Q * kParts * 128);
-  // bars[0] = weights landed; bars[1 + j] = A ready (tile j); bars[1 + NTILES + j] = accumulator ready
+  // bars[0] = weights landed; bars[1 + j] = accumulator ready (tile j)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * NTILES);
   TileInfo* tinfo = reinterpret_cast<TileInfo*>(tmem_slot + 2);
 
   const uint32_t bar_w = smem_u32(&bars[0]);
-  uint32_t bar_a[NTILES], bar_acc[NTILES];
+  uint32_t bar_acc[NTILES];
 #pragma unroll
-  for (int j = 0; j < NTILES; ++j) {
-    bar_a[j] = smem_u32(&bars[1 + j]);
-    bar_acc[j] = smem_u32(&bars[1 + NTILES + j]);
-  }
+  for (int j = 0; j < NTILES; ++j) bar_acc[j] = smem_u32(&bars[1 + j]);
 
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
 #pragma unroll
-    for (int j = 0; j < NTILES; ++j) {
-      mbar_init(bar_a[j], 4 * Q);    // one arrival per epilogue warp of the tile
-      mbar_init(bar_acc[j], 1);      // tcgen05.commit
-    }
+    for (int j = 0; j < NTILES; ++j) mbar_init(bar_acc[j], 1);      // tcgen05.commit
     fence_barrier_init();
   }
   if (threadIdx.x < NTILES) {
@@ -291,7 +286,7 @@ __global__ void __launch_bounds__(NTILES* Q * 128 + 32, 1) rollout_tc_kernel(con
     }
     tinfo[threadIdx.x] = info;
   }
-  if (is_ctrl) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -303,13 +298,14 @@ __global__ void __launch_bounds__(NTILES* Q * 128 + 32, 1) rollout_tc_kernel(con
   for (int j = 0; j < NTILES; ++j)
     if (tinfo[j].valid) { any_valid = true; member = tinfo[j].member; }
 
-  // (setmaxnreg register re-balancing between the control warp and the epilogue warpgroups was
-  //  tried and faulted at run time on sm_100a / CUDA 12.9; with the state in TMEM 96 registers
-  //  per thread are enough, so the kernel runs with the plain launch-bound allocation.)
-  if (warp >= kCtrlWarp) {
-    if (any_valid && is_ctrl) {
-      // =========================== control warp: TMA + MMA issue ===============================
-      if (lane == 0) {
+  // (A dedicated MMA warp fed by per-warp mbarrier arrivals, and setmaxnreg register re-balancing,
+  //  were the first designs: the polling warp cost issue slots and one extra wake-up per layer, and
+  //  setmaxnreg faulted at run time on sm_100a / CUDA 12.9. The tile-local barrier + elected issuer
+  //  below needs neither.)
+  {
+    if (any_valid) {
+      // weights of this member: one TMA bulk copy per layer, all onto bars[0]
+      if (threadIdx.x == 0) {
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(prm.w_bf16) +
                               (size_t)member * prm.w_bf16_member_bytes;
         mbar_expect_tx(bar_w, w_bytes);
@@ -319,37 +315,7 @@ __global__ void __launch_bounds__(NTILES* Q * 128 + 32, 1) rollout_tc_kernel(con
           bulk_g2s(smem_u32(w_smem + off), wsrc + off, nb, bar_w);
           off += nb;
         }
-        mbar_wait(bar_w, 0);
-        uint32_t ph[NTILES];
-#pragma unroll
-        for (int j = 0; j < NTILES; ++j) ph[j] = 0;
-        for (int t = 0; t < H; ++t) {
-          uint32_t woff = 0;
-          for (int l = 0; l <= L; ++l) {
-            const int ksteps = (l == 0) ? 4 : 8;             // K = 64 or 128, UMMA_K = 16
-#pragma unroll
-            for (int j = 0; j < NTILES; ++j) {
-              if (!tinfo[j].valid) continue;
-              mbar_wait(bar_a[j], ph[j]);
-              ph[j] ^= 1;
-              tc_fence_after();
-              const uint32_t a_base = smem_u32(a_smem + j * 2 * kAtomBytes);
-              const uint32_t b_base = smem_u32(w_smem + woff);
-              for (int k = 0; k < ksteps; ++k) {
-                const uint32_t koff = (uint32_t)(k >> 2) * kAtomBytes + (uint32_t)(k & 3) * 32;
-                umma_bf16(tmem_base + j * 128, umma_desc_sw128(a_base + koff),
-                          umma_desc_sw128(b_base + koff), kIdesc, k > 0 ? 1u : 0u);
-              }
-              umma_commit(bar_acc[j]);
-            }
-            woff += (l == 0) ? kAtomBytes : 2 * kAtomBytes;
-          }
-        }
       }
-      __syncwarp();
-    }
-  } else {
-    if (any_valid) {
       // ============ epilogue warps: Q threads per rollout row, each owns a column slice ============
       const int j = warp / (4 * Q);                       // tile of this warp
       const int wl = warp - j * 4 * Q;                    // warp within the tile
@@ -390,6 +356,29 @@ __global__ void __launch_bounds__(NTILES* Q * 128 + 32, 1) rollout_tc_kernel(con
                                  (uint32_t)(NTILES * 128 + j * 64);            // this row's state columns
         const float* s0_ptr = prm.states + (prm.state_per_row ? id.r_global : (int64_t)id.s) * prm.state_stride;
         const float* bh = bias_smem + L * 128;
+
+        // The tile's A operand for `layer` is complete once every thread of the tile has passed the
+        // named barrier below (each fenced its own writes to the async proxy first); the tile's
+        // elected thread then issues that layer's MMAs and commits them onto the tile's mbarrier.
+        const bool issuer = (wl == 0) && (lane == 0);
+        auto tile_sync_and_issue = [&](int layer) {
+          tc_fence_before();
+          fence_proxy_async();
+          named_bar_sync<kTileThreads>(2 + j);
+          if (issuer) {
+            tc_fence_after();
+            const int ksteps = (layer == 0) ? 4 : 8;          // K = 64 or 128, UMMA_K = 16
+            const uint32_t woff = (layer == 0) ? 0u : (uint32_t)(kAtomBytes + (layer - 1) * 2 * kAtomBytes);
+            const uint32_t a_base = smem_u32(a_smem + j * 2 * kAtomBytes);
+            const uint32_t b_base = smem_u32(w_smem + woff);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint32_t koff = (uint32_t)(k >> 2) * kAtomBytes + (uint32_t)(k & 3) * 32;
+              umma_bf16(tmem_base + j * 128, umma_desc_sw128(a_base + koff),
+                        umma_desc_sw128(b_base + koff), kIdesc, k > 0 ? 1u : 0u);
+            }
+            umma_commit(bar_acc[j]);
+          }
+        };
 
         // Which of this thread's 16-wide chunks intersect the goal slice / constrained slices
         // (warp-uniform bit masks, bit = sub-chunk), so that chunks outside every lidar do no scoring.
@@ -542,12 +531,6 @@ __global__ void __launch_bounds__(NTILES* Q * 128 + 32, 1) rollout_tc_kernel(con
             }
           }
           tmem_st_wait();
-          if (t_next < H) {                      // hand the next step's input to the tensor core first
-            tc_fence_before();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_a[j]);
-          }
           part[0] = gmin;
 #pragma unroll
           for (int q = 0; q < SIMBA_MAX_CONSTRAINTS; ++q)
@@ -572,10 +555,11 @@ __global__ void __launch_bounds__(NTILES* Q * 128 + 32, 1) rollout_tc_kernel(con
         RowScore rs;
         rs.cum = 0.0f; rs.costsum = 0.0f; rs.cmask = 0ull; rs.done = false; rs.dist = 0.0f; rs.cost = 0.0f;
         state_pass(std::true_type{}, std::false_type{}, 0, 0);
-        named_bar_sync<kTileThreads>(2 + j);
+        if (issuer) mbar_wait(bar_w, 0);                 // weights have landed before the first MMA
+        tile_sync_and_issue(0);                          // also orders the partials for combine()
         if (cgp == 0) combine(rs.dist, rs.cost);
-        // (the partials are next written after L+1 accumulator waits, each of which needs an A-ready
-        //  arrival from every warp of the tile, including the group-0 warps reading here)
+        // (the partials are next written after the tile has passed L more tile barriers, which the
+        //  group-0 threads reading here reach only after combine())
 
         uint32_t ph = 0;
         for (int t = 0; t < H; ++t) {
@@ -606,10 +590,7 @@ __global__ void __launch_bounds__(NTILES* Q * 128 + 32, 1) rollout_tc_kernel(con
                              pack_relu_bf16(f3.x, f3.y));
               }
             }
-            tc_fence_before();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_a[j]);
+            tile_sync_and_issue(l + 1);
           }
 
           // ---- Gaussian heads + state update + next input + partial minima (one fused pass) --------
@@ -619,8 +600,13 @@ __global__ void __launch_bounds__(NTILES* Q * 128 + 32, 1) rollout_tc_kernel(con
           if (prm.sampling_propagation) state_pass(std::false_type{}, std::true_type{}, t, t + 1);
           else state_pass(std::false_type{}, std::false_type{}, t, t + 1);
 
-          // ---- scoring of (s_t, s_{t+1}): safety_gym.py:110-166, per-row objective ------------------
-          named_bar_sync<kTileThreads>(2 + j);
+          // ---- next step's layer-0 MMA goes out first; then scoring of (s_t, s_{t+1}):
+          //      safety_gym.py:110-166, per-row objective ------------------------------------------------
+          if (t + 1 < H) {
+            tile_sync_and_issue(0);
+          } else {
+            named_bar_sync<kTileThreads>(2 + j);
+          }
           if (cgp == 0) {
             float next_dist, next_cost;
             combine(next_dist, next_cost);
@@ -651,7 +637,7 @@ __global__ void __launch_bounds__(NTILES* Q * 128 + 32, 1) rollout_tc_kernel(con
 
   tc_fence_before();
   __syncthreads();
-  if (is_ctrl) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -681,7 +667,7 @@ static cudaError_t launch_variant(const RolloutParams& prm, int n_tiles, cudaStr
     configured = smem;
   }
   const int grid = (n_tiles + NTILES - 1) / NTILES;
-  rollout_tc_kernel<NTILES, Q><<<grid, NTILES * Q * 128 + 32, smem, stream>>>(prm);
+  rollout_tc_kernel<NTILES, Q><<<grid, NTILES * Q * 128, smem, stream>>>(prm);
   return cudaGetLastError();
 }
 
