@@ -722,6 +722,8 @@ static int do_rollout_score(simba_planner_t* p, const float* states, const float
   prm.active = active;
   prm.row_return = row_return; prm.row_costmask = row_costmask; prm.row_costsum = row_costsum;
   prm.tc_tiles_per_cta = p->tiles_per_cta;
+  if (const char* tlp = getenv("SIMBA_TC_TIMELINE_PTR"))   // debug builds only (tools/tc_timeline.py)
+    prm.traj_out = reinterpret_cast<float*>(strtoull(tlp, nullptr, 10));
   if (p->cfg.precision == SIMBA_PREC_BF16_TC)
     CUDA_TRY(launch_rollout_tc(prm, prm.n_tiles, (cudaStream_t)stream));
   else

@@ -627,20 +627,27 @@ template <bool kFast>
 __global__ void philox_normals_kernel(uint64_t seed, uint32_t stream, uint32_t iteration,
                                       uint32_t t, uint32_t s, uint32_t first_row, int n_rows,
                                       int n_elems, float* out) {
-  const int JB = (n_elems + 3) / 4;
+  const int per = (stream == kStreamNoise) ? 8 : 4;       // NOISE: 8 normals per block (16-bit uniforms)
+  const int JB = (n_elems + per - 1) / per;
   const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (idx >= (long)n_rows * JB) return;
   const int row = (int)(idx / JB), j = (int)(idx % JB);
-  const float4 n = philox_normals<kFast>(seed, stream, s, iteration, t, first_row + row, (uint32_t)j);
-  const float z[4] = {n.x, n.y, n.z, n.w};
-  for (int q = 0; q < 4; ++q)
-    if (4 * j + q < n_elems) out[(long)row * n_elems + 4 * j + q] = z[q];
+  float z[8];
+  if (stream == kStreamNoise) {
+    philox_noise8<kFast>(seed, s, iteration, t, first_row + row, (uint32_t)j, z);
+  } else {
+    const float4 n = philox_normals<kFast>(seed, stream, s, iteration, t, first_row + row, (uint32_t)j);
+    z[0] = n.x; z[1] = n.y; z[2] = n.z; z[3] = n.w;
+  }
+  for (int q = 0; q < per; ++q)
+    if (per * j + q < n_elems) out[(long)row * n_elems + per * j + q] = z[q];
 }
 
 cudaError_t launch_philox_normals(uint64_t seed, int stream, int iteration, int t, int s,
                                   int first_row, int n_rows, int n_elems, int fast, float* out,
                                   cudaStream_t st) {
-  const long total = (long)n_rows * ((n_elems + 3) / 4);
+  const int per = (stream == (int)kStreamNoise) ? 8 : 4;
+  const long total = (long)n_rows * ((n_elems + per - 1) / per);
   const int blocks = (int)((total + 255) / 256);
   if (fast)
     philox_normals_kernel<true><<<blocks, 256, 0, st>>>(seed, stream, iteration, t, s, first_row,

@@ -90,6 +90,37 @@ __device__ __forceinline__ float4 normals4(uint4 b) {
   return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
 }
 
+// NOISE stream: 8 normals per Philox block from 16-bit uniforms (see oracle/philox.py). Every
+// 32-bit word gives one Box-Muller pair: u_a from the low half, u_b from the high half.
+__device__ __forceinline__ float u01_16(uint32_t h) {   // (h + 0.5) * 2^-16, exact in fp32
+  return fmaf((float)h, 1.52587890625e-05f, 7.62939453125e-06f);
+}
+template <bool kFast>
+__device__ __forceinline__ void normals8(uint4 b, float (&z)[8]) {
+  const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float ua = u01_16(w[i] & 0xffffu), ub = u01_16(w[i] >> 16);
+    float r, sn, cs;
+    if (kFast) {
+      asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * __log2f(ua)));
+      __sincosf(6.283185307179586f * ub, &sn, &cs);
+    } else {
+      r = sqrtf(-2.0f * logf(ua));
+      sincospif(2.0f * ub, &sn, &cs);
+    }
+    z[2 * i] = r * cs;
+    z[2 * i + 1] = r * sn;
+  }
+}
+
+template <bool kFast>
+__device__ __forceinline__ void philox_noise8(uint64_t seed, uint32_t s, uint32_t iteration,
+                                              uint32_t t, uint32_t row, uint32_t block8, float (&z)[8]) {
+  const uint4 ctr = make_uint4(block8, row, t | (iteration << 16), s | (kStreamNoise << 28));
+  normals8<kFast>(philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))), z);
+}
+
 __device__ __forceinline__ uint2 philox_key(uint64_t seed) {
   return make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
 }

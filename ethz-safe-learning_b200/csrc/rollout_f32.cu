@@ -201,35 +201,33 @@ __global__ void __launch_bounds__(NT) rollout_f32_kernel(const RolloutParams prm
 
     // ---- s_{t+1} = s_t + (mu + sqrt(var) * eps | mu)   (mlp_ensemble.py:192-193,
     //      transition_model.py:75) -------------------------------------------------------------
-    const int JB = (O + 3) / 4;
+    const int JB = (O + 7) / 8;                 // one Philox NOISE block = 8 consecutive outputs
     for (int item = tid; item < TM * JB; item += NT) {
       const int j = item / TM, row = item - j * TM;
       if (row >= tile.count) continue;
       const int64_t rgl = row_meta[1 * TM + row];
       const int s = (int)row_meta[4 * TM + row];
-      float e4[4] = {0.f, 0.f, 0.f, 0.f};
+      float e8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       const bool need_eps = prm.sampling_propagation || prm.sample_out != nullptr;
       if (need_eps) {
         if (prm.eps != nullptr) {
           const float* ep = prm.eps + (((int64_t)s * H + t) * ((int64_t)g.P * g.N) + rgl) * O;
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (4 * j + q < O) e4[q] = ep[4 * j + q];
+          for (int q = 0; q < 8; ++q)
+            if (8 * j + q < O) e8[q] = ep[8 * j + q];
         } else {
-          const float4 z = philox_normals<false>(seed, kStreamNoise, (uint32_t)s,
-                                                 (uint32_t)prm.iteration, (uint32_t)t,
-                                                 (uint32_t)rgl, (uint32_t)j);
-          e4[0] = z.x; e4[1] = z.y; e4[2] = z.z; e4[3] = z.w;
+          philox_noise8<false>(seed, (uint32_t)s, (uint32_t)prm.iteration, (uint32_t)t, (uint32_t)rgl,
+                               (uint32_t)j, e8);
         }
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int o = 4 * j + q;
+      for (int q = 0; q < 8; ++q) {
+        const int o = 8 * j + q;
         if (o >= O) break;
         const float mu = in[o * TM + row];
         const float var = __fadd_rn(softplus_tf(in[(O + o) * TM + row]), 1e-4f);
         const float sd = sqrtf(var);
-        const float smp = __fadd_rn(mu, __fmul_rn(sd, e4[q]));
+        const float smp = __fadd_rn(mu, __fmul_rn(sd, e8[q]));
         const float d = prm.sampling_propagation ? smp : mu;
         state[row * OS + o] = __fadd_rn(state[row * OS + o], d);
         if (prm.mu_out != nullptr) {

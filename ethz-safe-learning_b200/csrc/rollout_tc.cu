@@ -35,6 +35,18 @@
 
 namespace simba {
 
+// Debug timeline (compile with -DSIMBA_TC_TIMELINE): two threads of CTA 0 stamp clock64() at phase
+// boundaries into prm.traj_out (a scratch buffer handed in by tools/tc_timeline.py).
+#ifdef SIMBA_TC_TIMELINE
+#define TL(ev)                                                                                   \
+  do {                                                                                           \
+    if (tl_who >= 0 && blockIdx.x == 0)                                                          \
+      reinterpret_cast<long long*>(prm.traj_out)[(tl_who * 64 + tl_t) * 64 + (ev)] = clock64();  \
+  } while (0)
+#else
+#define TL(ev) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kU = 128;                 // hidden width this kernel covers
@@ -204,24 +216,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
-// softplus on the MUFU path, accurate for very negative inputs (var-head biases of trained models)
+// softplus on the MUFU path: ln(1 + e^x) = lg2(1 + ex2(x * log2 e)) * ln 2. The rounding of 1 + e
+// costs at most 6e-8 absolute, i.e. <= 6e-4 relative to the variance because of its 1e-4 floor
+// (mlp_ensemble.py:30) — far inside the bf16 path's tolerance.
 __device__ __forceinline__ float softplus_fast(float x) {
-  const float e = __expf(fminf(x, 30.0f));
-  const float small = e * (1.0f - e * (0.5f - e * 0.33333334f));
-  const float big = __logf(1.0f + e);
-  const float sp = e < 0.03f ? small : big;
-  return x > 15.0f ? x : sp;
-}
-
-// Box-Muller on the MUFU path (same counter map and uniforms as the accurate path in common.cuh)
-__device__ __forceinline__ float4 normals4_fast(uint4 b) {
-  const float ua = u01(b.x), ub = u01(b.y), uc = u01(b.z), ud = u01(b.w);
-  const float ra = sqrt_approx(-1.3862943611198906f * __log2f(ua));
-  const float rb = sqrt_approx(-1.3862943611198906f * __log2f(uc));
-  float sa, ca, sb, cb;
-  __sincosf(6.283185307179586f * ub, &sa, &ca);
-  __sincosf(6.283185307179586f * ud, &sb, &cb);
-  return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
+  const float e = exp2f(fminf(x, 80.0f) * 1.4426950408889634f);
+  return __log2f(1.0f + e) * 0.6931471805599453f;
 }
 
 struct TileInfo {
@@ -380,6 +380,16 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
           }
         };
 
+        // Accumulator-ready wait: one warp of the tile polls the mbarrier, the other warps block at a
+        // named barrier (BAR.SYNC waits in hardware and costs no issue slots, unlike a try_wait loop).
+        uint32_t ph = 0;
+        auto wait_accumulator = [&]() {
+          if (wl == 0) mbar_wait(bar_acc[j], ph);
+          ph ^= 1;
+          named_bar_sync<kTileThreads>(2 + NTILES + j);
+          tc_fence_after();
+        };
+
         // Which of this thread's 16-wide chunks intersect the goal slice / constrained slices
         // (warp-uniform bit masks, bit = sub-chunk), so that chunks outside every lidar do no scoring.
         uint32_t has_goal = 0, has_con = 0;
@@ -391,6 +401,45 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
           for (int q = 0; q < sc.n_constraints; ++q)
             if (sc.con_begin[q] < hi && sc.con_end[q] > lo) has_con |= 1u << (sub * SIMBA_MAX_CONSTRAINTS + q);
         }
+
+        // the thread that owns the action columns of the layer-0 input prefetches a_{t+1} one step
+        // ahead, so the L2 latency is off the critical path (A <= 4 on this path)
+        const bool owns_actions = (o_base + OW > O) && (o_base < O + A);
+        float act_pf[4] = {0.f, 0.f, 0.f, 0.f};
+        auto prefetch_actions = [&](int tn) {
+          if (owns_actions && row_ok && tn < H) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              if (a < A) act_pf[a] = act_ptr[tn * A + a];
+          }
+        };
+
+        // N(0,1) draws of this thread's OW outputs for the current step. They depend only on
+        // (seed, iteration, t, row, o), not on the network, so they are produced one Philox block
+        // (8 normals) at a time right after this tile's MMAs have been issued for a hidden layer,
+        // i.e. in the shadow of the tensor-core latency instead of inside the head epilogue.
+        float e_pre[OW];
+#pragma unroll
+        for (int i = 0; i < OW; ++i) e_pre[i] = 0.0f;
+        auto make_noise = [&](int call, int t) {              // call in [0, OW / 8)
+#pragma unroll
+          for (int c = 0; c < OW / 8; ++c) {
+            if (c != call) continue;
+            const int o0 = o_base + c * 8;
+            if (o0 >= O) continue;
+            if (prm.eps != nullptr) {
+              const float* ep = prm.eps + (((int64_t)id.s * H + t) * ((int64_t)g.P * g.N) + id.r_global) * O;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) e_pre[c * 8 + q] = (o0 + q < O) ? ep[o0 + q] : 0.0f;
+            } else {
+              float z[8];
+              philox_noise8<true>(seed, (uint32_t)id.s, (uint32_t)prm.iteration, (uint32_t)t,
+                                  (uint32_t)id.r_global, (uint32_t)(o0 >> 3), z);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) e_pre[c * 8 + q] = z[q];
+            }
+          }
+        };
 
         // One pass over this thread's OW state dims in 16-wide chunks. kFirst: load s_0 from global
         // memory; otherwise apply the Gaussian-head update of step t (mlp_ensemble.py:189-193,
@@ -404,9 +453,6 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
           float cmin[SIMBA_MAX_CONSTRAINTS];
 #pragma unroll
           for (int q = 0; q < SIMBA_MAX_CONSTRAINTS; ++q) cmin[q] = INFINITY;
-          const float* ep = nullptr;
-          if (!kFirst && kSample && prm.eps != nullptr)
-            ep = prm.eps + (((int64_t)id.s * H + t) * ((int64_t)g.P * g.N) + id.r_global) * O;
 #pragma unroll
           for (int sub = 0; sub < OW / 16; ++sub) {
             const int oc = o_base + sub * 16;               // first state dim of this chunk
@@ -422,39 +468,28 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
               tmem_ld16(t_state + oc, st);
               tmem_ld_wait();
 #pragma unroll
-              for (int jb = 0; jb < 4; ++jb) {
-                const int o0 = oc + jb * 4;
-                const float4 bm = *reinterpret_cast<const float4*>(bh + o0);
-                const float bmu[4] = {bm.x, bm.y, bm.z, bm.w};
-                float d[4];
+              for (int jb = 0; jb < 2; ++jb) {                  // one Philox NOISE block = 8 outputs
+                const int o0 = oc + jb * 8;
+                const float4 bm0 = *reinterpret_cast<const float4*>(bh + o0);
+                const float4 bm1 = *reinterpret_cast<const float4*>(bh + o0 + 4);
+                const float bmu[8] = {bm0.x, bm0.y, bm0.z, bm0.w, bm1.x, bm1.y, bm1.z, bm1.w};
+                float d[8];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) d[q] = __uint_as_float(vm[jb * 4 + q]) + bmu[q];
+                for (int q = 0; q < 8; ++q) d[q] = __uint_as_float(vm[jb * 8 + q]) + bmu[q];
                 if (kSample && o0 < O) {
-                  float e4[4] = {0.f, 0.f, 0.f, 0.f};
-                  if (ep != nullptr) {
+                  const float4 bv0 = *reinterpret_cast<const float4*>(bh + 64 + o0);
+                  const float4 bv1 = *reinterpret_cast<const float4*>(bh + 64 + o0 + 4);
+                  const float bvar[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                      if (o0 + q < O) e4[q] = ep[o0 + q];
-                  } else {
-                    const uint4 bits = philox4x32_10(
-                        make_uint4((uint32_t)(o0 >> 2), (uint32_t)id.r_global,
-                                   (uint32_t)t | ((uint32_t)prm.iteration << 16),
-                                   (uint32_t)id.s | (kStreamNoise << 28)), philox_key(seed));
-                    const float4 z = normals4_fast(bits);
-                    e4[0] = z.x; e4[1] = z.y; e4[2] = z.z; e4[3] = z.w;
-                  }
-                  const float4 bv = *reinterpret_cast<const float4*>(bh + 64 + o0);
-                  const float bvar[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const float var = softplus_fast(__uint_as_float(vv[jb * 4 + q]) + bvar[q]) + 1e-4f;
-                    d[q] = fmaf(sqrt_approx(var), e4[q], d[q]);
+                  for (int q = 0; q < 8; ++q) {
+                    const float var = softplus_fast(__uint_as_float(vv[jb * 8 + q]) + bvar[q]) + 1e-4f;
+                    d[q] = fmaf(sqrt_approx(var), e_pre[sub * 16 + jb * 8 + q], d[q]);
                   }
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float old = __uint_as_float(st[jb * 4 + q]);
-                  sv[jb * 4 + q] = (full || o0 + q < O) ? old + d[q] : old;
+                for (int q = 0; q < 8; ++q) {
+                  const float old = __uint_as_float(st[jb * 8 + q]);
+                  sv[jb * 8 + q] = (full || o0 + q < O) ? old + d[q] : old;
                 }
               }
             }
@@ -517,7 +552,7 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
                 for (int i = 0; i < 16; ++i) {
                   const int o = oc + i;
                   float xin = sv[i];                                             // zero beyond O
-                  if (o >= O && o < O + A) xin = row_ok ? act_ptr[t_next * A + (o - O)] : 0.0f;
+                  if (o >= O && o < O + A) xin = act_pf[(o - O) & 3];            // prefetched a_{t_next}
                   x[i] = fmaf(xin, scale_smem[o], scale_smem[64 + o]);           // padded k: a = b = 0
                 }
               }
@@ -554,6 +589,7 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
 
         RowScore rs;
         rs.cum = 0.0f; rs.costsum = 0.0f; rs.cmask = 0ull; rs.done = false; rs.dist = 0.0f; rs.cost = 0.0f;
+        prefetch_actions(0);
         state_pass(std::true_type{}, std::false_type{}, 0, 0);
         if (issuer) mbar_wait(bar_w, 0);                 // weights have landed before the first MMA
         tile_sync_and_issue(0);                          // also orders the partials for combine()
@@ -561,13 +597,20 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
         // (the partials are next written after the tile has passed L more tile barriers, which the
         //  group-0 threads reading here reach only after combine())
 
-        uint32_t ph = 0;
+#ifdef SIMBA_TC_TIMELINE
+        const int tl_who = (j == 0 && lane == 0) ? (wl == 0 ? 0 : (wl == 4 * Q - 1 ? 1 : -1)) : -1;
+        int tl_t = 0;
+#endif
         for (int t = 0; t < H; ++t) {
+#ifdef SIMBA_TC_TIMELINE
+          tl_t = t;
+#endif
+          TL(0);
+          prefetch_actions(t + 1);
           // ---- hidden layers: TMEM -> +bias, ReLU, bf16 -> next A operand -----------------------
           for (int l = 0; l < L; ++l) {
-            mbar_wait(bar_acc[j], ph);
-            ph ^= 1;
-            tc_fence_after();
+            wait_accumulator();
+            TL(1 + l * 4);
             const float* bl = bias_smem + l * 128;
 #pragma unroll
             for (int cc = 0; cc < HC; ++cc) {
@@ -590,20 +633,29 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
                              pack_relu_bf16(f3.x, f3.y));
               }
             }
+            TL(2 + l * 4);
             tile_sync_and_issue(l + 1);
+            if (prm.sampling_propagation) {
+              // spread the OW / 8 Philox blocks over the hidden layers (the last layer takes the rest)
+#pragma unroll
+              for (int c = 0; c < OW / 8; ++c)
+                if ((c < L - 1 ? c : L - 1) == l) make_noise(c, t);
+            }
+            TL(3 + l * 4);
           }
 
           // ---- Gaussian heads + state update + next input + partial minima (one fused pass) --------
-          mbar_wait(bar_acc[j], ph);
-          ph ^= 1;
-          tc_fence_after();
+          wait_accumulator();
+          TL(40);
           if (prm.sampling_propagation) state_pass(std::false_type{}, std::true_type{}, t, t + 1);
           else state_pass(std::false_type{}, std::false_type{}, t, t + 1);
 
           // ---- next step's layer-0 MMA goes out first; then scoring of (s_t, s_{t+1}):
           //      safety_gym.py:110-166, per-row objective ------------------------------------------------
+          TL(41);
           if (t + 1 < H) {
             tile_sync_and_issue(0);
+            TL(42);
           } else {
             named_bar_sync<kTileThreads>(2 + j);
           }
@@ -625,6 +677,7 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
             rs.dist = next_dist;
             rs.cost = next_cost;
           }
+          TL(43);
         }
         if (cgp == 0 && row_ok && prm.row_return != nullptr) {
           prm.row_return[id.out] = rs.cum;
@@ -642,7 +695,7 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
 
 // ---- host side ------------------------------------------------------------------------------------
 bool rollout_tc_supported(int O, int A, int L, int U, int H) {
-  return U == kU && O >= 1 && O <= kMaxO && O + A <= 64 && L >= 1 && L <= 6 && H >= 1 && H <= 64;
+  return U == kU && O >= 1 && O <= kMaxO && O + A <= 64 && A <= 4 && L >= 1 && L <= 6 && H >= 1 && H <= 64;
 }
 
 static size_t tc_smem_bytes(int L, int ntiles, int q) {

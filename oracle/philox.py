@@ -17,9 +17,15 @@ Counter map (must match csrc/philox.cuh):
         c3 = state index s | (stream << 28)
     streams: ACTION = 1 (elements = flattened (h, a)), NOISE = 2 (elements = observation
     dims o), FINAL = 3 (elements = action dims a).
-Uniforms:  u = ((x >> 8) + 0.5) * 2**-24   (fp32 arithmetic, never 0)
-Normals :  Box-Muller on (x0, x1) and (x2, x3):
-           z_even = sqrt(-2 ln u_a) * cos(2 pi u_b),  z_odd = sqrt(-2 ln u_a) * sin(2 pi u_b)
+ACTION / FINAL streams (4 normals per Philox block, 24-bit uniforms):
+  Uniforms:  u = ((x >> 8) + 0.5) * 2**-24   (fp32 arithmetic, never 0)
+  Normals :  Box-Muller on (x0, x1) and (x2, x3):
+             z_even = sqrt(-2 ln u_a) * cos(2 pi u_b),  z_odd = sqrt(-2 ln u_a) * sin(2 pi u_b)
+NOISE stream (8 normals per Philox block, 16-bit uniforms — the rollout draws 60 of these per
+transition, so the Philox cost per normal is halved): every 32-bit word x gives one pair
+  u_a = ((x & 0xffff) + 0.5) * 2**-16,  u_b = ((x >> 16) + 0.5) * 2**-16   (exact in fp32)
+  z_even = sqrt(-2 ln u_a) * cos(2 pi u_b),  z_odd = sqrt(-2 ln u_a) * sin(2 pi u_b)
+  c0 is then the index of the block of 8 consecutive observation dims; |z| <= 4.85.
 The oracle evaluates the Box-Muller formula in float64 and rounds once to float32; the
 device evaluates it in fp32 (a few ulp away) — tests state that tolerance.
 """
@@ -74,14 +80,25 @@ def normals_from_bits(x):
     return z.astype(np.float32)
 
 
+def normals8_from_bits(x):
+    """(..., 4) uint32 -> (..., 8) float32 normals: the NOISE-stream contract (16-bit uniforms)."""
+    x = np.asarray(x, dtype=np.uint32)
+    ua = ((x & np.uint32(0xFFFF)).astype(np.float64) + 0.5) * 2.0 ** -16
+    ub = ((x >> np.uint32(16)).astype(np.float64) + 0.5) * 2.0 ** -16
+    r = np.sqrt(-2.0 * np.log(ua))
+    th = 2.0 * np.pi * ub
+    z = np.stack([r * np.cos(th), r * np.sin(th)], axis=-1)          # (..., 4, 2)
+    return z.reshape(x.shape[:-1] + (8,)).astype(np.float32)
+
+
 def _key(seed):
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     return np.array([seed & 0xFFFFFFFF, seed >> 32], dtype=np.uint32)
 
 
-def _normals(seed, n_elems, c1, c2, c3):
+def _normals(seed, n_elems, c1, c2, c3, per_block=4):
     """Normals for elements 0..n_elems-1 over broadcast index arrays c1/c2/c3 -> (..., n_elems)."""
-    nblk = (n_elems + 3) // 4
+    nblk = (n_elems + per_block - 1) // per_block
     c1, c2, c3 = np.broadcast_arrays(np.asarray(c1, np.uint32), np.asarray(c2, np.uint32),
                                      np.asarray(c3, np.uint32))
     shape = c1.shape
@@ -90,8 +107,9 @@ def _normals(seed, n_elems, c1, c2, c3):
     ctr[..., 1] = c1[..., None]
     ctr[..., 2] = c2[..., None]
     ctr[..., 3] = c3[..., None]
-    z = normals_from_bits(philox4x32(ctr, _key(seed)))
-    return z.reshape(shape + (nblk * 4,))[..., :n_elems]
+    bits = philox4x32(ctr, _key(seed))
+    z = normals_from_bits(bits) if per_block == 4 else normals8_from_bits(bits)
+    return z.reshape(shape + (nblk * per_block,))[..., :n_elems]
 
 
 def action_normals(seed, iteration, n_samples, horizon, act_dim, state_index=0, first_candidate=0):
@@ -107,7 +125,7 @@ def noise_normals(seed, iteration, horizon, rows, obs_dim, state_index=0):
     rows = np.asarray(rows, dtype=np.uint32)
     t = np.arange(horizon, dtype=np.uint32)[:, None]
     return _normals(seed, obs_dim, rows[None, :], t | np.uint32(iteration << 16),
-                    np.uint32(state_index | (STREAM_NOISE << 28)))
+                    np.uint32(state_index | (STREAM_NOISE << 28)), per_block=8)
 
 
 def final_normals(seed, act_dim, state_index=0):
