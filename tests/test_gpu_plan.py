@@ -169,3 +169,66 @@ def test_fused_update_kernel_is_bit_identical_to_separate_kernels(precision):
     assert np.array_equal(f[0], u[0]) and f[1] == u[1]
     assert np.array_equal(f[2], u[2]) and np.array_equal(f[3], u[3]) and np.array_equal(f[4], u[4])
     assert f[5] == u[5] and 1 <= f[5] <= c['I']
+
+
+def test_wide_model_c5_reward_only_vs_safety_aware():
+    """BASELINE configs[4]: 10-member ensemble, 4x400 hidden, horizon 50 (fp32 kernel; the bf16
+    tcgen05 kernel covers units == 128 and reports SIMBA_ERR_UNSUPPORTED for this shape)."""
+    from simba_b200 import SimbaError, _lib, synthetic
+    c = helpers.workload('c5', N=40, K=5, I=2)                  # full model / horizon, small population
+    z, eps, zf = synthetic.make_draws(c['I'], 1, c['N'], c['H'], c['A'], c['P'], c['O'])
+    with pytest.raises(SimbaError) as e:
+        helpers.cuda_policy(c, 'penalty', precision='bf16').build()
+    assert e.value.code == -6
+    for objective in ('reward', 'penalty'):
+        pol = helpers.cuda_policy(c, objective, precision='fp32')
+        pol.set_external_draws(z, eps, zf)
+        action, score = pol.do_generate_action(c['state'])
+        tr = so.Trace()
+        a0, s0, n0 = helpers.oracle_planner(c, objective).do_generate_action(c['state'], z[:, 0], eps[:, 0], zf[0], tr)
+        elite = pol.buffer(_lib.BUF_ELITE, torch.int32).cpu().numpy()
+        mu = pol.buffer(_lib.BUF_MU).cpu().numpy().reshape(c['H'], c['A'])
+        assert np.array_equal(elite, tr[-1]['elite'])
+        assert np.allclose(mu, tr[-1]['mu'], rtol=1e-4, atol=1e-6)
+        assert np.isclose(score, s0, rtol=1e-4, atol=1e-4)
+
+
+def test_c3_shape_particle_map_reduced_population():
+    """BASELINE configs[2] dims (P = 32, H = 30, E = 5 -> B % E != 0, 'particle' member map) at a
+    reduced population so the oracle finishes in seconds."""
+    from simba_b200 import SimbaError, _lib, synthetic
+    c = helpers.workload('c3', N=96, K=10, I=2)
+    with pytest.raises(SimbaError) as e:                        # the reference's tf.split would raise too
+        helpers.cuda_policy(c, 'penalty', precision='fp32', member_map='split').build()
+    assert e.value.code == -2
+    z, eps, zf = synthetic.make_draws(c['I'], 1, c['N'], c['H'], c['A'], c['P'], c['O'])
+    pol = helpers.cuda_policy(c, 'penalty', precision='fp32', member_map='particle')
+    pol.set_external_draws(z, eps, zf)
+    action, score = pol.do_generate_action(c['state'])
+    tr = so.Trace()
+    a0, s0, n0 = helpers.oracle_planner(c, 'penalty', member_map='particle').do_generate_action(
+        c['state'], z[:, 0], eps[:, 0], zf[0], tr)
+    elite = pol.buffer(_lib.BUF_ELITE, torch.int32).cpu().numpy()
+    assert np.array_equal(elite, tr[-1]['elite'])
+    assert np.allclose(action, a0, rtol=1e-4, atol=1e-5) and np.isclose(score, s0, rtol=1e-4, atol=1e-4)
+    assert pol.count_threshold == 3                             # P = 32 -> c_max = 3
+
+
+def test_shipped_config_simple_lidar_layout_both_precisions():
+    """The reference's shipped config (PointSimpleGoal1: 5-bin lidars, O = 22, E = 15, H = 8,
+    P = 45; config/policies.yaml:11-20) — exercises the generic sensor layout of both kernels."""
+    from simba_b200 import _lib, synthetic
+    c = helpers.workload('shipped', sensors=synthetic.POINTSIMPLEGOAL1_SENSORS, N=100, K=10, I=3)
+    z, eps, zf = synthetic.make_draws(c['I'], 1, c['N'], c['H'], c['A'], c['P'], c['O'])
+    tr = so.Trace()
+    a0, s0, n0 = helpers.oracle_planner(c, 'penalty').do_generate_action(c['state'], z[:, 0], eps[:, 0], zf[0], tr)
+    pol = helpers.cuda_policy(c, 'penalty', precision='fp32')
+    pol.set_external_draws(z, eps, zf)
+    a, s = pol.do_generate_action(c['state'])
+    assert np.array_equal(pol.buffer(_lib.BUF_ELITE, torch.int32).cpu().numpy(), tr[-1]['elite'])
+    assert np.allclose(a, a0, rtol=1e-4, atol=1e-5) and np.isclose(s, s0, rtol=1e-4, atol=1e-4)
+    polb = helpers.cuda_policy(c, 'penalty', precision='bf16')
+    polb.set_external_draws(z, eps, zf)
+    ab, sb = polb.do_generate_action(c['state'])
+    assert np.all(np.isfinite(ab)) and abs(sb - s0) < 5e-2
+    assert pol.count_threshold == 5                             # P = 45 -> c_max = 5
