@@ -28,6 +28,7 @@
 //     exchange and one named barrier per step and tile.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -75,7 +76,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
+#ifdef SIMBA_TC_SPIN
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+#endif
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity), "r"(kSuspendHintNs)
@@ -128,6 +133,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (activations) is read from tensor memory, so one
+// MMA streams only the weight tile from shared memory (half the SMEM traffic of the SS form)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
@@ -165,6 +181,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
       "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
       "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() {
@@ -237,8 +259,10 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
   constexpr int kEpiThreads = NTILES * kTileThreads;
   constexpr int OW = 64 / Q;          // head outputs (= state dims = layer-0 K elements) per thread
   constexpr int HC = 4 / Q;           // 32-column accumulator chunks per thread in hidden layers
-  // TMEM columns: NTILES x 128 accumulator columns, then NTILES x 64 state columns (power of two)
-  constexpr int kTmemCols = (NTILES * 192 <= 256) ? 256 : 512;
+  // TMEM columns per tile: 128 fp32 accumulator columns, 64 fp32 state columns and 64 columns that
+  // hold the bf16 A operand (128 K-elements, two per 32-bit column). Layout:
+  // [NTILES x 128 acc][NTILES x 64 state][NTILES x 64 A]  ->  256 / 512 columns (power of two)
+  constexpr int kTmemCols = NTILES * 256;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const RowGeom& g = prm.g;
   const int L = prm.L;
@@ -249,12 +273,12 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
   // ---- shared memory carve-up (base is 1024-aligned: required by SWIZZLE_128B) -------------------
   const uint32_t w_bytes = kAtomBytes + (uint32_t)L * 2 * kAtomBytes;     // layer 0: 1 atom; others: 2
   uint8_t* w_smem = smem_raw;
-  uint8_t* a_smem = w_smem + w_bytes;                                      // [NTILES][2 atoms]
-  float* bias_smem = reinterpret_cast<float*>(a_smem + NTILES * 2 * kAtomBytes);   // [(L+1)][128]
+  float* bias_smem = reinterpret_cast<float*>(w_smem + w_bytes);           // [(L+1)][128]
   float* scale_smem = bias_smem + (L + 1) * 128;                           // [2][64]: a, b of x*a+b
   float* pen_smem = scale_smem + 128;                                      // [kParts][64]: 0 in slice, +inf outside
-  float* part_smem = pen_smem + kParts * 64;                               // [NTILES][Q][kParts][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(part_smem + NTILES * Q * kParts * 128);
+  const int nparts = 1 + prm.scorer.n_constraints;                         // goal + constrained lidars
+  float* part_smem = pen_smem + kParts * 64;                               // [NTILES][Q][nparts][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part_smem + NTILES * Q * nparts * 128);
   // bars[0] = weights landed; bars[1 + j] = accumulator ready (tile j)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * NTILES);
   TileInfo* tinfo = reinterpret_cast<TileInfo*>(tmem_slot + 2);
@@ -341,19 +365,19 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
         const bool row_ok = r < ti.count;
         const RowId id = decode_row(g, ti.member, ti.k0 + (row_ok ? r : 0));
         const uint64_t seed = prm.seed_ptr ? *prm.seed_ptr : prm.seed;
-        const uint32_t a_row = smem_u32(a_smem + j * 2 * kAtomBytes) + (uint32_t)r * 128;
-        const uint32_t swz = (uint32_t)(r & 7);
         const uint32_t t_lane = tmem_base + ((uint32_t)((wl & 3) * 32) << 16) + (uint32_t)j * 128;
         const float* act_ptr = prm.actions + ((int64_t)id.s * g.N + id.i_global) * prm.action_stride;
         const bool done_first = objective_done_first(prm.objective);
         const simba_scorer_t& sc = prm.scorer;
         const int o_base = cgp * OW;                      // first state dim / head output of this thread
-        float* part = part_smem + ((j * Q + cgp) * kParts) * 128 + r;         // [kParts] stride 128
-        const float* part_row = part_smem + (j * Q * kParts) * 128 + r;       // group 0 base of this row
+        float* part = part_smem + ((j * Q + cgp) * nparts) * 128 + r;         // [nparts] stride 128
+        const float* part_row = part_smem + (j * Q * nparts) * 128 + r;       // group 0 base of this row
         const float D = sc.lidar_max_dist;
 
         const uint32_t t_state = tmem_base + ((uint32_t)((wl & 3) * 32) << 16) +
                                  (uint32_t)(NTILES * 128 + j * 64);            // this row's state columns
+        const uint32_t t_a = tmem_base + ((uint32_t)((wl & 3) * 32) << 16) +
+                             (uint32_t)(NTILES * 192 + j * 64);                // this row's A-operand columns
         const float* s0_ptr = prm.states + (prm.state_per_row ? id.r_global : (int64_t)id.s) * prm.state_stride;
         const float* bh = bias_smem + L * 128;
 
@@ -362,19 +386,19 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
         // elected thread then issues that layer's MMAs and commits them onto the tile's mbarrier.
         const bool issuer = (wl == 0) && (lane == 0);
         auto tile_sync_and_issue = [&](int layer) {
+          tmem_st_wait();                                     // this thread's A-operand stores have landed
           tc_fence_before();
-          fence_proxy_async();
           named_bar_sync<kTileThreads>(2 + j);
           if (issuer) {
             tc_fence_after();
             const int ksteps = (layer == 0) ? 4 : 8;          // K = 64 or 128, UMMA_K = 16
             const uint32_t woff = (layer == 0) ? 0u : (uint32_t)(kAtomBytes + (layer - 1) * 2 * kAtomBytes);
-            const uint32_t a_base = smem_u32(a_smem + j * 2 * kAtomBytes);
+            const uint32_t a_base = tmem_base + (uint32_t)(NTILES * 192 + j * 64);   // lane 0, A columns
             const uint32_t b_base = smem_u32(w_smem + woff);
             for (int k = 0; k < ksteps; ++k) {
               const uint32_t koff = (uint32_t)(k >> 2) * kAtomBytes + (uint32_t)(k & 3) * 32;
-              umma_bf16(tmem_base + j * 128, umma_desc_sw128(a_base + koff),
-                        umma_desc_sw128(b_base + koff), kIdesc, k > 0 ? 1u : 0u);
+              umma_bf16_ts(tmem_base + j * 128, a_base + (uint32_t)k * 8,           // 16 bf16 = 8 columns
+                           umma_desc_sw128(b_base + koff), kIdesc, k > 0 ? 1u : 0u);
             }
             umma_commit(bar_acc[j]);
           }
@@ -433,8 +457,13 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
               for (int q = 0; q < 8; ++q) e_pre[c * 8 + q] = (o0 + q < O) ? ep[o0 + q] : 0.0f;
             } else {
               float z[8];
+#ifdef ABL_NO_PHILOX
+#pragma unroll
+              for (int q = 0; q < 8; ++q) z[q] = 0.3f + 0.01f * (float)(q + t);
+#else
               philox_noise8<true>(seed, (uint32_t)id.s, (uint32_t)prm.iteration, (uint32_t)t,
                                   (uint32_t)id.r_global, (uint32_t)(o0 >> 3), z);
+#endif
 #pragma unroll
               for (int q = 0; q < 8; ++q) e_pre[c * 8 + q] = z[q];
             }
@@ -482,8 +511,13 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
                   const float bvar[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
 #pragma unroll
                   for (int q = 0; q < 8; ++q) {
+#ifdef ABL_NO_SOFTPLUS
+                    const float var = (__uint_as_float(vv[jb * 8 + q]) + bvar[q]) * 1e-6f + 3e-4f;
+                    d[q] = fmaf(var, e_pre[sub * 16 + jb * 8 + q], d[q]);
+#else
                     const float var = softplus_fast(__uint_as_float(vv[jb * 8 + q]) + bvar[q]) + 1e-4f;
                     d[q] = fmaf(sqrt_approx(var), e_pre[sub * 16 + jb * 8 + q], d[q]);
+#endif
                   }
                 }
 #pragma unroll
@@ -500,8 +534,13 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
               tmem_st16(t_state + oc, st);
             }
             // ---- partial lidar minima, only for chunks that intersect a slice -----------------
+#ifdef ABL_NO_SCORE
+            const uint32_t con_bits = 0;
+            if (false) {
+#else
             const uint32_t con_bits = (has_con >> (sub * SIMBA_MAX_CONSTRAINTS)) & 0xFu;
             if (((has_goal >> sub) & 1u) | con_bits) {
+#endif
               if (sc.goal_dist_index >= 0) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
@@ -556,13 +595,10 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
                   x[i] = fmaf(xin, scale_smem[o], scale_smem[64 + o]);           // padded k: a = b = 0
                 }
               }
+              uint32_t pk[8];
 #pragma unroll
-              for (int c = 0; c < 2; ++c) {
-                const uint32_t chunk = (uint32_t)(oc / 8 + c);
-                st_shared_v4(a_row + ((chunk ^ swz) << 4), pack_bf16(x[8 * c], x[8 * c + 1]),
-                             pack_bf16(x[8 * c + 2], x[8 * c + 3]), pack_bf16(x[8 * c + 4], x[8 * c + 5]),
-                             pack_bf16(x[8 * c + 6], x[8 * c + 7]));
-              }
+              for (int c = 0; c < 8; ++c) pk[c] = pack_bf16(x[2 * c], x[2 * c + 1]);
+              tmem_st8(t_a + oc / 2, pk);                   // K elements [oc, oc + 16) of the layer-0 input
             }
           }
           tmem_st_wait();
@@ -575,12 +611,12 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
         auto combine = [&](float& dist, float& cost) {
           float gmin = INFINITY;
 #pragma unroll
-          for (int c = 0; c < Q; ++c) gmin = fminf(gmin, part_row[(c * kParts) * 128]);
+          for (int c = 0; c < Q; ++c) gmin = fminf(gmin, part_row[(c * nparts) * 128]);
           float cst = 0.0f;
           for (int q = 0; q < sc.n_constraints; ++q) {
             float m = INFINITY;
 #pragma unroll
-            for (int c = 0; c < Q; ++c) m = fminf(m, part_row[(c * kParts + 1 + q) * 128]);
+            for (int c = 0; c < Q; ++c) m = fminf(m, part_row[(c * nparts + 1 + q) * 128]);
             cst += (m <= sc.con_size[q]) ? 1.0f : 0.0f;
           }
           dist = gmin;
@@ -616,9 +652,17 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
             for (int cc = 0; cc < HC; ++cc) {
               const int c = cgp * HC + cc;                 // 32-column chunk of the accumulator row
               uint32_t v[32];
+#ifdef ABL_HALF_LDTM
+              if (cc == 0) { tmem_ld32(t_lane + c * 32, v); tmem_ld_wait(); }
+              else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0x3f000000u + (uint32_t)(i + l);
+              }
+#else
               tmem_ld32(t_lane + c * 32, v);
               tmem_ld_wait();
-              const uint32_t atom = a_row + (uint32_t)(c >> 1) * kAtomBytes;
+#endif
+              uint32_t pk[16];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const float4 b0 = *reinterpret_cast<const float4*>(bl + c * 32 + q * 8);
@@ -627,11 +671,12 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
                 const float2 f1 = add2(v[q * 8 + 2], v[q * 8 + 3], make_float2(b0.z, b0.w));
                 const float2 f2 = add2(v[q * 8 + 4], v[q * 8 + 5], make_float2(b1.x, b1.y));
                 const float2 f3 = add2(v[q * 8 + 6], v[q * 8 + 7], make_float2(b1.z, b1.w));
-                const uint32_t chunk = (uint32_t)((c & 1) * 4 + q);
-                st_shared_v4(atom + ((chunk ^ swz) << 4), pack_relu_bf16(f0.x, f0.y),
-                             pack_relu_bf16(f1.x, f1.y), pack_relu_bf16(f2.x, f2.y),
-                             pack_relu_bf16(f3.x, f3.y));
+                pk[q * 4 + 0] = pack_relu_bf16(f0.x, f0.y);
+                pk[q * 4 + 1] = pack_relu_bf16(f1.x, f1.y);
+                pk[q * 4 + 2] = pack_relu_bf16(f2.x, f2.y);
+                pk[q * 4 + 3] = pack_relu_bf16(f3.x, f3.y);
               }
+              tmem_st16(t_a + c * 16, pk);                  // K elements [32c, 32c + 32) of this row
             }
             TL(2 + l * 4);
             tile_sync_and_issue(l + 1);
@@ -698,20 +743,19 @@ bool rollout_tc_supported(int O, int A, int L, int U, int H) {
   return U == kU && O >= 1 && O <= kMaxO && O + A <= 64 && A <= 4 && L >= 1 && L <= 6 && H >= 1 && H <= 64;
 }
 
-static size_t tc_smem_bytes(int L, int ntiles, int q) {
+static size_t tc_smem_bytes(int L, int ntiles, int q, int nparts) {
   size_t b = (size_t)kAtomBytes + (size_t)L * 2 * kAtomBytes;      // weights
-  b += (size_t)ntiles * 2 * kAtomBytes;                            // A operands
   b += (size_t)(L + 1) * 128 * sizeof(float);                      // biases
   b += 128 * sizeof(float);                                        // scaler
   b += kParts * 64 * sizeof(float);                                // slice penalty table
-  b += (size_t)ntiles * q * kParts * 128 * sizeof(float);          // partial minima exchange
+  b += (size_t)ntiles * q * nparts * 128 * sizeof(float);          // partial minima exchange
   b += (1 + 2 * ntiles) * sizeof(uint64_t) + 2 * sizeof(uint32_t) + ntiles * sizeof(TileInfo);
   return b + 1024;                                                 // alignment slack
 }
 
 template <int NTILES, int Q>
 static cudaError_t launch_variant(const RolloutParams& prm, int n_tiles, cudaStream_t stream) {
-  const size_t smem = tc_smem_bytes(prm.L, NTILES, Q);
+  const size_t smem = tc_smem_bytes(prm.L, NTILES, Q, 1 + prm.scorer.n_constraints);
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(rollout_tc_kernel<NTILES, Q>,
