@@ -408,9 +408,15 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
         // named barrier (BAR.SYNC waits in hardware and costs no issue slots, unlike a try_wait loop).
         uint32_t ph = 0;
         auto wait_accumulator = [&]() {
-          if (wl == 0) mbar_wait(bar_acc[j], ph);
+          if (NTILES == 1) {
+            // latency configuration (one tile, SM otherwise idle): every warp polls, which saves the
+            // barrier hop after the poller wakes up
+            mbar_wait(bar_acc[j], ph);
+          } else {
+            if (wl == 0) mbar_wait(bar_acc[j], ph);
+            named_bar_sync<kTileThreads>(2 + NTILES + j);
+          }
           ph ^= 1;
-          named_bar_sync<kTileThreads>(2 + NTILES + j);
           tc_fence_after();
         };
 
