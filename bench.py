@@ -306,6 +306,15 @@ def main():
         extras['error'] = repr(e)
     if extras:
         line['extras'] = extras
+    if 'c4' in extras and 'tflops_per_gpu' in extras['c4']:
+        # the same kernel at a shape that fills the GPU (BASELINE configs[3], 1024 states per call):
+        # whole planning calls, so it includes the small CEM kernels (< 1 % of the time there)
+        tf = extras['c4']['tflops_per_gpu']
+        line['roofline_large'] = {"kernel": "rollout_tc_kernel<2,2>" if precision == 'bf16' else "rollout_f32_kernel",
+                                  "workload": "configs[3]: %d states x C1 per GPU" % extras['c4']['states_per_call_per_gpu'],
+                                  "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
+                                  "frac": tf / peak_tf, "traffic": None,
+                                  "note": "plan-level: algorithmic flops of the call / CUDA-event time of the call"}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = time_cpu_planner(c)
