@@ -437,6 +437,7 @@ struct simba_planner {
   Tile* d_tiles = nullptr;
   int tile_rows = 0;
   int tiles_per_cta = 1;
+  bool use_pdl = false;        // programmatic dependent launch between rollout and fused update kernels
   bool fused_update = false;   // one rank, N <= 1024: reduce+select+refit(+next sample | finalize) in one kernel
   int c_max = -1;
   // workspace
@@ -573,6 +574,7 @@ extern "C" int simba_planner_create(simba_model_t* model, const simba_planner_co
     build_tiles(p->geom, p->tile_rows, p->tiles, 2);
   }
   p->fused_update = cfg->world_size == 1 && cfg->n_samples <= 1024 && getenv("SIMBA_B200_NO_FUSE") == nullptr;
+  p->use_pdl = p->fused_update && cfg->precision == SIMBA_PREC_BF16_TC && getenv("SIMBA_B200_NO_PDL") == nullptr;
   p->c_max = beta_count_threshold(cfg->particles, cfg->posterior_mean_threshold, cfg->prior_mu,
                                   cfg->prior_sigma);
 
@@ -704,7 +706,7 @@ extern "C" int simba_sample_actions(simba_planner_t* p, const float* mu, const f
 static int do_rollout_score(simba_planner_t* p, const float* states, const float* actions,
                             const float* eps, uint64_t seed, const uint64_t* seed_ptr,
                             int32_t iteration, const int32_t* active, float* row_return,
-                            uint64_t* row_costmask, float* row_costsum, void* stream) {
+                            uint64_t* row_costmask, float* row_costsum, void* stream, bool pdl = false) {
   if (!p || !states || !actions || !row_return || !row_costmask || !row_costsum)
     return fail(SIMBA_ERR_BAD_CONFIG, "null argument");
   RolloutParams prm{};
@@ -722,6 +724,7 @@ static int do_rollout_score(simba_planner_t* p, const float* states, const float
   prm.active = active;
   prm.row_return = row_return; prm.row_costmask = row_costmask; prm.row_costsum = row_costsum;
   prm.tc_tiles_per_cta = p->tiles_per_cta;
+  prm.pdl = pdl ? 1 : 0;
   if (const char* tlp = getenv("SIMBA_TC_TIMELINE_PTR"))   // debug builds only (tools/tc_timeline.py)
     prm.traj_out = reinterpret_cast<float*>(strtoull(tlp, nullptr, 10));
   if (p->cfg.precision == SIMBA_PREC_BF16_TC)
@@ -871,10 +874,12 @@ static int enqueue_plan(simba_planner* p, cudaStream_t st, int* n_launches) {
     if (rc) return rc; ++launches;
     for (int it = 0; it < c.iterations; ++it) {
       const float* eps = p->ext_eps ? p->ext_eps + (size_t)it * S * c.horizon * B * O : nullptr;
+      // the first rollout follows the plain sample kernel; later ones follow a PDL-aware update kernel
       rc = do_rollout_score(p, p->d_states, p->actions, eps, 0, sp, it, p->active, p->row_ret,
-                            p->row_cmask, p->row_csum, st);
+                            p->row_cmask, p->row_csum, st, p->use_pdl && it > 0);
       if (rc) return rc; ++launches;
       UpdateParams u{};
+      u.pdl = p->use_pdl ? 1 : 0;
       u.reduce = make_reduce_params(p, p->row_ret, p->row_cmask, p->row_csum, p->active, p->pairs_local);
       u.select = make_select_params(p, p->pairs_local, p->actions, p->active, p->elite, nullptr,
                                     p->best_action, p->best_score);

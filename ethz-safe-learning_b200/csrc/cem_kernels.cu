@@ -401,6 +401,10 @@ cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t st) {
 // Selection is rank-by-counting: thread i owns candidate i and counts the keys that beat it.
 // =============================================================================================
 __global__ void __launch_bounds__(kRefitThreads) cem_update_kernel(UpdateParams u) {
+  // PDL: the next rollout may start its prologue (TMEM allocation, barrier init) now; this kernel
+  // needs the previous rollout's row outputs, so it waits for that grid first.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int s = blockIdx.x;
   const int tid = threadIdx.x;
   extern __shared__ float sh[];                       // refit scratch, then keys / elite list
@@ -477,8 +481,17 @@ cudaError_t launch_cem_update(const UpdateParams& u, cudaStream_t st) {
   const int groups = kRefitThreads / HA > 0 ? kRefitThreads / HA : 1;
   size_t smem = (size_t)((groups + 2) * HA + 1) * sizeof(float);
   smem = (smem + 7) / 8 * 8 + (size_t)u.select.N * 8 + (size_t)u.select.K * 4 + 16;
-  cem_update_kernel<<<u.refit.S, kRefitThreads, smem, st>>>(u);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(u.refit.S);
+  cfg.blockDim = dim3(kRefitThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = u.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, cem_update_kernel, u);
 }
 
 // plan bookkeeping: reset mu/sigma/best/active at the start of a plan (cem_mpc.py:36-42)

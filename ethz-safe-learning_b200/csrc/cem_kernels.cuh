@@ -77,6 +77,7 @@ struct UpdateParams {                 // fused k8 + k9 + k10 (+ next k1 | k11): 
   SampleParams sample;                // next iteration's sampling (ignored when last)
   FinalizeParams finalize;            // used when last
   int32_t last;
+  int32_t pdl;                        // launch with programmatic stream serialization
   float* out_score;
   int32_t* out_iters;
 };

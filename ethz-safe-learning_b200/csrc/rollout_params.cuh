@@ -24,6 +24,7 @@ struct RolloutParams {
   int64_t w_bf16_member_bytes;
   const float* bias_tc;       // [E][L+1][128] fp32 (heads: mu bias at [0, O), var bias at [64, 64+O))
   int32_t tc_tiles_per_cta;   // 1 (latency: small populations) or 2 (MMA / epilogue ping-pong)
+  int32_t pdl;                // launch with programmatic stream serialization (fused plan path)
   float tc_scale_a[64];       // bf16 path: x_scaled[k] = fma(x[k], a[k], b[k]); zero beyond O + A
   float tc_scale_b[64];
   // scaler (transition_model.py:79-87): x_scaled = (x - smin) / sdelta, sdelta already holds 1.01

@@ -207,6 +207,14 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
                : "memory");
 }
+// Programmatic dependent launch (PDL): let the next kernel in the stream start its prologue while
+// this one runs, and wait for the previous kernel's results only where they are first needed.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait_prior_grid() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 __device__ __forceinline__ float sqrt_approx(float x) {
   float r;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -283,12 +291,17 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
 #pragma unroll
   for (int j = 0; j < NTILES; ++j) bar_acc[j] = smem_u32(&bars[1 + j]);
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
 #pragma unroll
     for (int j = 0; j < NTILES; ++j) mbar_init(bar_acc[j], 1);      // tcgen05.commit
     fence_barrier_init();
   }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  // everything above is independent of the previous kernel (the CEM update that wrote the actions
+  // and the active flags); from here on its results are needed
+  pdl_wait_prior_grid();
   if (threadIdx.x < NTILES) {
     const int ti = blockIdx.x * NTILES + threadIdx.x;
     TileInfo info{0, 0, 0, 0};
@@ -305,7 +318,6 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
     }
     tinfo[threadIdx.x] = info;
   }
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -757,8 +769,17 @@ static cudaError_t launch_variant(const RolloutParams& prm, int n_tiles, cudaStr
     configured = smem;
   }
   const int grid = (n_tiles + NTILES - 1) / NTILES;
-  rollout_tc_kernel<NTILES, Q><<<grid, NTILES * Q * 128, smem, stream>>>(prm);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NTILES * Q * 128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = prm.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, rollout_tc_kernel<NTILES, Q>, prm);
 }
 
 cudaError_t launch_rollout_tc(const RolloutParams& prm, int n_tiles, cudaStream_t stream) {
