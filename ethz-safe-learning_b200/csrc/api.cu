@@ -75,6 +75,7 @@ struct simba_model {
   std::vector<float> smin, smax;
   int scale_on = 1;
   bool scaler_set = false, committed = false;
+  uint64_t generation = 0;     // bumped by every commit; planners re-capture their graph when it changes
   // device images
   float* d_w_f32 = nullptr;
   float* d_bias_f32 = nullptr;
@@ -190,7 +191,11 @@ extern "C" int simba_model_commit(simba_model_t* m) {
                   i % (L + 2));
   if (!m->scaler_set) return fail(SIMBA_ERR_NOT_READY, "scaler not set");
   CUDA_TRY(cudaSetDevice(m->device));
-  model_free_device(m);
+  // Device images are allocated on the first commit and updated IN PLACE afterwards (their sizes
+  // are fixed by the immutable model config): planners that captured a CUDA graph keep valid
+  // pointers when the weights or the scaler change (e.g. after every model.fit of the agent loop).
+  // The copies below are synchronous, so they are ordered after earlier launches on any stream
+  // only by the caller's own synchronisation (generate_action is synchronous).
 
   // ---- fp32 chunk stream: layer -> column block (128) -> k chunk (16), heads fused as N = 2*O ---
   const int KC = kF32ChunkRows, NB = kF32ChunkCols;
@@ -230,9 +235,10 @@ extern "C" int simba_model_commit(simba_model_t* m) {
       boff += Np;
     }
   }
-  CUDA_TRY(cudaMalloc(&m->d_w_f32, w.size() * sizeof(float)));
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (!m->d_w_f32) CUDA_TRY(cudaMalloc(&m->d_w_f32, w.size() * sizeof(float)));
   CUDA_TRY(cudaMemcpy(m->d_w_f32, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMalloc(&m->d_bias_f32, b.size() * sizeof(float)));
+  if (!m->d_bias_f32) CUDA_TRY(cudaMalloc(&m->d_bias_f32, b.size() * sizeof(float)));
   CUDA_TRY(cudaMemcpy(m->d_bias_f32, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
 
   // ---- bf16 UMMA image (only the shapes the tcgen05 kernel covers) -------------------------------
@@ -265,7 +271,7 @@ extern "C" int simba_model_commit(simba_model_t* m) {
       }
     }
     m->w_bf16_member_bytes = member_bytes;
-    CUDA_TRY(cudaMalloc(&m->d_w_bf16, img.size() * 2));
+    if (!m->d_w_bf16) CUDA_TRY(cudaMalloc(&m->d_w_bf16, img.size() * 2));
     CUDA_TRY(cudaMemcpy(m->d_w_bf16, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
     std::vector<float> bt((size_t)E * (L + 1) * 128, 0.0f);
     for (int e = 0; e < E; ++e) {
@@ -276,7 +282,7 @@ extern "C" int simba_model_commit(simba_model_t* m) {
         bt[((size_t)e * (L + 1) + L) * 128 + 64 + n] = m->biases[e * (L + 2) + L + 1][n];
       }
     }
-    CUDA_TRY(cudaMalloc(&m->d_bias_tc, bt.size() * sizeof(float)));
+    if (!m->d_bias_tc) CUDA_TRY(cudaMalloc(&m->d_bias_tc, bt.size() * sizeof(float)));
     CUDA_TRY(cudaMemcpy(m->d_bias_tc, bt.data(), bt.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
 
@@ -292,13 +298,14 @@ extern "C" int simba_model_commit(simba_model_t* m) {
     m->tc_scale_a[k] = k < IN ? (m->scale_on ? inv[k] : 1.0f) : 0.0f;
     m->tc_scale_b[k] = k < IN ? (m->scale_on ? -m->smin[k] * inv[k] : 0.0f) : 0.0f;
   }
-  CUDA_TRY(cudaMalloc(&m->d_smin, IN * sizeof(float)));
-  CUDA_TRY(cudaMalloc(&m->d_sdelta, IN * sizeof(float)));
-  CUDA_TRY(cudaMalloc(&m->d_sinv, IN * sizeof(float)));
+  if (!m->d_smin) CUDA_TRY(cudaMalloc(&m->d_smin, IN * sizeof(float)));
+  if (!m->d_sdelta) CUDA_TRY(cudaMalloc(&m->d_sdelta, IN * sizeof(float)));
+  if (!m->d_sinv) CUDA_TRY(cudaMalloc(&m->d_sinv, IN * sizeof(float)));
   CUDA_TRY(cudaMemcpy(m->d_smin, m->smin.data(), IN * sizeof(float), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(m->d_sdelta, delta.data(), IN * sizeof(float), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(m->d_sinv, inv.data(), IN * sizeof(float), cudaMemcpyHostToDevice));
   m->committed = true;
+  ++m->generation;
   return SIMBA_OK;
 }
 
@@ -458,6 +465,7 @@ struct simba_planner {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   int launches_per_plan = 0;
+  uint64_t graph_generation = 0;   // model generation the graph was captured against
   NcclComm comm = nullptr;
 };
 
@@ -925,7 +933,12 @@ static int enqueue_plan(simba_planner* p, cudaStream_t st, int* n_launches) {
 }
 
 static int ensure_graph(simba_planner* p) {
-  if (p->graph_exec) return SIMBA_OK;
+  if (!p->model->committed) return fail(SIMBA_ERR_NOT_READY, "model has uncommitted changes");
+  if (p->graph_exec && p->graph_generation == p->model->generation) return SIMBA_OK;
+  // kernel parameters (scaler constants, flags) are baked into the graph nodes: a re-committed
+  // model needs a fresh capture (weights themselves are updated in place and would not)
+  if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+  if (p->graph) { cudaGraphDestroy(p->graph); p->graph = nullptr; }
   CUDA_TRY(cudaStreamBeginCapture(p->own_stream, cudaStreamCaptureModeThreadLocal));
   int launches = 0;
   int rc = enqueue_plan(p, p->own_stream, &launches);
@@ -936,6 +949,7 @@ static int ensure_graph(simba_planner* p) {
   p->graph = g;
   CUDA_TRY(cudaGraphInstantiate(&p->graph_exec, p->graph, 0));
   p->launches_per_plan = launches;
+  p->graph_generation = p->model->generation;
   return SIMBA_OK;
 }
 

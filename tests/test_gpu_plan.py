@@ -232,3 +232,27 @@ def test_shipped_config_simple_lidar_layout_both_precisions():
     ab, sb = polb.do_generate_action(c['state'])
     assert np.all(np.isfinite(ab)) and abs(sb - s0) < 5e-2
     assert pol.count_threshold == 5                             # P = 45 -> c_max = 5
+
+
+def test_weight_and_scaler_updates_reach_an_already_used_planner():
+    """The agent loop refits the model between planning calls (mbrl_agent.py:41-53): new weights /
+    statistics must take effect on the next generate_action without rebuilding the policy."""
+    from simba_b200 import synthetic
+    c = helpers.workload('tiny')
+    for precision in ('fp32', 'bf16'):
+        pol = helpers.cuda_policy(c, 'penalty', precision=precision)
+        a1, s1 = pol.do_generate_action(c['state'], seed=9)
+        w2 = synthetic.make_weights(c['E'], c['L'], c['U'], c['O'], c['A'], seed=123)
+        for e in range(c['E']):
+            pol.model.model.ensemble[e].set_weights(w2[e])
+        a2, s2 = pol.do_generate_action(c['state'], seed=9)
+        fresh = helpers.cuda_policy(dict(c, weights=w2), 'penalty', precision=precision)
+        a3, s3 = fresh.do_generate_action(c['state'], seed=9)
+        assert np.array_equal(a2, a3) and s2 == s3 and not np.array_equal(a1, a2)
+        lo, hi = c['smin'].copy(), c['smax'].copy()
+        hi[:c['O']] = 3.0
+        pol.model.set_statistics(lo, hi)
+        fresh.model.set_statistics(lo, hi)
+        a4, s4 = pol.do_generate_action(c['state'], seed=9)
+        a5, s5 = fresh.do_generate_action(c['state'], seed=9)
+        assert np.array_equal(a4, a5) and s4 == s5 and not np.array_equal(a4, a2)
