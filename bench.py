@@ -368,11 +368,21 @@ def bench_c3(synthetic, torch, dist, lib, _lib, precision, world, rank):
     """BASELINE configs[2]: population 65536, 32 particles, horizon 30, sharded over the ranks with one
     NCCL all-gather of (return, cost) per iteration. E=5 does not divide P=32 (the reference's tf.split
     would raise) -> member_map='particle'."""
-    import ctypes as C
     c = synthetic.make_workload('c3')
-    pol = synthetic.build_policy(c, 'penalty', precision=precision, member_map='particle', seed=21,
-                                 rank=rank, world_size=world)
-    pol.build()
+    pol, ok = None, 1.0
+    try:
+        pol = synthetic.build_policy(c, 'penalty', precision=precision, member_map='particle', seed=21,
+                                     rank=rank, world_size=world)
+        pol.build()
+    except Exception:
+        ok = 0.0
+    if world > 1:
+        # every rank must reach the collective NCCL init, or none: agree first
+        flag = torch.tensor([ok], device='cuda')
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = float(flag.cpu()[0])
+    if ok < 1.0:
+        return {"skipped": "planner construction failed on at least one rank"}
     if world > 1:
         from simba_b200 import distributed as sd
         sd.init_population_sharding(pol)
