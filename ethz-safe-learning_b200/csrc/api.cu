@@ -81,6 +81,7 @@ struct simba_model {
   float* d_bias_f32 = nullptr;
   void* d_w_bf16 = nullptr;
   float* d_bias_tc = nullptr;
+  void* d_bias_k16 = nullptr;   // per member, per layer: UMMA B tile [128 n][16 k] (no swizzle) holding the bias as bf16 hi + lo
   float tc_scale_a[64] = {0}, tc_scale_b[64] = {0};
   float* d_smin = nullptr;
   float* d_sdelta = nullptr;
@@ -120,8 +121,8 @@ extern "C" int simba_model_create(const simba_model_config_t* cfg, simba_model_t
 }
 
 static void model_free_device(simba_model* m) {
-  cudaFree(m->d_w_f32); cudaFree(m->d_bias_f32); cudaFree(m->d_w_bf16); cudaFree(m->d_bias_tc);
-  m->d_bias_tc = nullptr;
+  cudaFree(m->d_w_f32); cudaFree(m->d_bias_f32); cudaFree(m->d_w_bf16); cudaFree(m->d_bias_tc); cudaFree(m->d_bias_k16);
+  m->d_bias_tc = nullptr; m->d_bias_k16 = nullptr;
   cudaFree(m->d_smin); cudaFree(m->d_sdelta); cudaFree(m->d_sinv);
   m->d_w_f32 = m->d_bias_f32 = m->d_smin = m->d_sdelta = m->d_sinv = nullptr;
   m->d_w_bf16 = nullptr;
@@ -284,6 +285,25 @@ extern "C" int simba_model_commit(simba_model_t* m) {
     }
     if (!m->d_bias_tc) CUDA_TRY(cudaMalloc(&m->d_bias_tc, bt.size() * sizeof(float)));
     CUDA_TRY(cudaMemcpy(m->d_bias_tc, bt.data(), bt.size() * sizeof(float), cudaMemcpyHostToDevice));
+    // bias as one more K = 16 block of every layer's GEMM: B[n][0] = bf16(b[n]), B[n][1] = bf16(b[n] - hi),
+    // K-major, SWIZZLE_NONE canonical layout: 8-row x 16-byte core matrices, the two K halves 128 B apart
+    // (leading byte offset), 8-row groups 256 B apart (stride byte offset) -> 4 KB per layer
+    std::vector<uint16_t> bk((size_t)E * (L + 1) * 2048, 0);
+    for (int e = 0; e < E; ++e)
+      for (int l = 0; l <= L; ++l)
+        for (int n = 0; n < 128; ++n) {
+          const float bv = bt[((size_t)e * (L + 1) + l) * 128 + n];
+          const uint16_t hi = f32_to_bf16_rne(bv);
+          uint32_t hb = (uint32_t)hi << 16;
+          float hf;
+          memcpy(&hf, &hb, 4);
+          const uint16_t lo = f32_to_bf16_rne(bv - hf);
+          const size_t base = ((size_t)e * (L + 1) + l) * 2048 + (size_t)(n / 8) * 128 + (size_t)(n % 8) * 8;
+          bk[base + 0] = hi;
+          bk[base + 1] = lo;
+        }
+    if (!m->d_bias_k16) CUDA_TRY(cudaMalloc(&m->d_bias_k16, bk.size() * 2));
+    CUDA_TRY(cudaMemcpy(m->d_bias_k16, bk.data(), bk.size() * 2, cudaMemcpyHostToDevice));
   }
 
   // ---- scaler: delta = max - min, 1.01 where delta < 1e-5 (transition_model.py:85-86) ----------
@@ -320,6 +340,7 @@ static void fill_model_params(const simba_model* m, RolloutParams& prm) {
   prm.w_bf16 = m->d_w_bf16;
   prm.w_bf16_member_bytes = m->w_bf16_member_bytes;
   prm.bias_tc = m->d_bias_tc;
+  prm.bias_k16 = m->d_bias_k16;
   memcpy(prm.tc_scale_a, m->tc_scale_a, sizeof(prm.tc_scale_a));
   memcpy(prm.tc_scale_b, m->tc_scale_b, sizeof(prm.tc_scale_b));
   prm.tc_tiles_per_cta = 1;

@@ -22,6 +22,7 @@ struct RolloutParams {
   // bf16 image: per member, per layer pre-swizzled UMMA B tiles (see pack_bf16 in api.cu)
   const void* w_bf16;
   int64_t w_bf16_member_bytes;
+  const void* bias_k16;       // [E][L+1][4096 B] bias K-blocks (see simba_model_commit)
   const float* bias_tc;       // [E][L+1][128] fp32 (heads: mu bias at [0, O), var bias at [64, 64+O))
   int32_t tc_tiles_per_cta;   // 1 (latency: small populations) or 2 (MMA / epilogue ping-pong)
   int32_t pdl;                // launch with programmatic stream serialization (fused plan path)

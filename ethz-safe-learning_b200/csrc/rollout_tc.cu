@@ -235,6 +235,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
   return d;
 }
+// K-major, SWIZZLE_NONE tile of [128 rows][16 k] bf16: 8-row x 16-byte core matrices, K halves 128 B apart
+// (leading byte offset), 8-row groups 256 B apart (stride byte offset). Used for the bias K-block.
+__device__ __forceinline__ uint64_t umma_desc_k16_noswizzle(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(128 >> 4) << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;                                            // layout type 0 = SWIZZLE_NONE
+}
 // instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -276,8 +286,9 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
   // ---- shared memory carve-up (base is 1024-aligned: required by SWIZZLE_128B) -------------------
   const uint32_t w_bytes = kAtomBytes + (uint32_t)L * 2 * kAtomBytes;     // layer 0: 1 atom; others: 2
   uint8_t* w_smem = smem_raw;
-  float* bias_smem = reinterpret_cast<float*>(w_smem + w_bytes);           // [(L+1)][128]
-  float* scale_smem = bias_smem + (L + 1) * 128;                           // [2][64]: a, b of x*a+b
+  uint8_t* biask_smem = w_smem + w_bytes;                                  // [(L+1)][4096]: bias K-blocks (B operand)
+  uint8_t* ones_smem = biask_smem + (L + 1) * 4096;                        // [4096]: A operand of the bias K-step
+  float* scale_smem = reinterpret_cast<float*>(ones_smem + 4096);          // [2][64]: a, b of x*a+b
   float* pen_smem = scale_smem + 128;                                      // [kParts][64]: 0 in slice, +inf outside
   const int nparts = 1 + prm.scorer.n_constraints;                         // goal + constrained lidars
   float* part_smem = pen_smem + kParts * 64;                               // [NTILES][Q][nparts][128]
@@ -339,13 +350,16 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
       if (threadIdx.x == 0) {
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(prm.w_bf16) +
                               (size_t)member * prm.w_bf16_member_bytes;
-        mbar_expect_tx(bar_w, w_bytes);
+        const uint32_t bk_bytes = (uint32_t)(L + 1) * 4096u;
+        mbar_expect_tx(bar_w, w_bytes + bk_bytes);
         uint32_t off = 0;
         for (int l = 0; l <= L; ++l) {
           const uint32_t nb = (l == 0) ? kAtomBytes : 2 * kAtomBytes;
           bulk_g2s(smem_u32(w_smem + off), wsrc + off, nb, bar_w);
           off += nb;
         }
+        bulk_g2s(smem_u32(biask_smem), reinterpret_cast<const uint8_t*>(prm.bias_k16) + (size_t)member * bk_bytes,
+                 bk_bytes, bar_w);
       }
       // ============ epilogue warps: Q threads per rollout row, each owns a column slice ============
       const int j = warp / (4 * Q);                       // tile of this warp
@@ -355,8 +369,13 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
       const TileInfo ti = tinfo[j];
       // biases + scaler of this member -> shared (all epilogue threads of the CTA cooperate)
       {
-        const float* bsrc = prm.bias_tc + (size_t)member * (L + 1) * 128;
-        for (int i = threadIdx.x; i < (L + 1) * 128; i += kEpiThreads) bias_smem[i] = bsrc[i];
+        // A operand of the bias K-step: ones[m][0] = ones[m][1] = 1, rest 0 (same core-matrix layout)
+        for (int i = threadIdx.x; i < 1024; i += kEpiThreads) {
+          const int byte = i * 4;                           // [16 groups][2 K halves][8 rows][16 B]
+          const bool first = ((byte & 255) < 128) && ((byte & 15) == 0);   // K half 0, elements 0 and 1
+          reinterpret_cast<uint32_t*>(ones_smem)[i] = first ? 0x3F803F80u : 0u;
+        }
+        fence_proxy_async();                                // generic-proxy writes -> visible to the MMA
         for (int i = threadIdx.x; i < 64; i += kEpiThreads) {
           scale_smem[i] = prm.tc_scale_a[i];
           scale_smem[64 + i] = prm.tc_scale_b[i];
@@ -386,7 +405,6 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
         const uint32_t t_a = tmem_base + ((uint32_t)((wl & 3) * 32) << 16) +
                              (uint32_t)(NTILES * 192 + j * 64);                // this row's A-operand columns
         const float* s0_ptr = prm.states + (prm.state_per_row ? id.r_global : (int64_t)id.s) * prm.state_stride;
-        const float* bh = bias_smem + L * 128;
 
         // The tile's A operand for `layer` is complete once every thread of the tile has passed the
         // named barrier below (each fenced its own writes to the async proxy first); the tile's
@@ -407,6 +425,9 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
               umma_bf16_ts(tmem_base + j * 128, a_base + (uint32_t)k * 8,           // 16 bf16 = 8 columns
                            umma_desc_sw128(b_base + koff), kIdesc, k > 0 ? 1u : 0u);
             }
+            // + bias: ones[128 x 16] * biasK[16 x 128] (bf16 hi + lo rows), both operands from SMEM
+            umma_bf16(tmem_base + j * 128, umma_desc_k16_noswizzle(smem_u32(ones_smem)),
+                      umma_desc_k16_noswizzle(smem_u32(biask_smem + layer * 4096)), kIdesc, 1u);
             umma_commit(bar_acc[j]);
           }
         };
@@ -512,23 +533,17 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
 #pragma unroll
               for (int jb = 0; jb < CW / 8; ++jb) {             // one Philox NOISE block = 8 outputs
                 const int o0 = oc + jb * 8;
-                const float4 bm0 = *reinterpret_cast<const float4*>(bh + o0);
-                const float4 bm1 = *reinterpret_cast<const float4*>(bh + o0 + 4);
-                const float bmu[8] = {bm0.x, bm0.y, bm0.z, bm0.w, bm1.x, bm1.y, bm1.z, bm1.w};
-                float d[8];
+                float d[8];                                  // mu (bias folded into the GEMM)
 #pragma unroll
-                for (int q = 0; q < 8; ++q) d[q] = __uint_as_float(vm[jb * 8 + q]) + bmu[q];
+                for (int q = 0; q < 8; ++q) d[q] = __uint_as_float(vm[jb * 8 + q]);
                 if (kSample && o0 < O) {
-                  const float4 bv0 = *reinterpret_cast<const float4*>(bh + 64 + o0);
-                  const float4 bv1 = *reinterpret_cast<const float4*>(bh + 64 + o0 + 4);
-                  const float bvar[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
 #pragma unroll
                   for (int q = 0; q < 8; ++q) {
 #ifdef ABL_NO_SOFTPLUS
-                    const float var = (__uint_as_float(vv[jb * 8 + q]) + bvar[q]) * 1e-6f + 3e-4f;
+                    const float var = __uint_as_float(vv[jb * 8 + q]) * 1e-6f + 3e-4f;
                     d[q] = fmaf(var, e_pre[sub * CW + jb * 8 + q], d[q]);
 #else
-                    const float var = softplus_fast(__uint_as_float(vv[jb * 8 + q]) + bvar[q]) + 1e-4f;
+                    const float var = softplus_fast(__uint_as_float(vv[jb * 8 + q])) + 1e-4f;
                     d[q] = fmaf(sqrt_approx(var), e_pre[sub * CW + jb * 8 + q], d[q]);
 #endif
                   }
@@ -660,27 +675,16 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
           for (int l = 0; l < L; ++l) {
             wait_accumulator();
             TL(1 + l * 4);
-            const float* bl = bias_smem + l * 128;
 #pragma unroll
             for (int cc = 0; cc < HC; ++cc) {
               const int col0 = (cgp * HC + cc) * HW;       // first accumulator column of this chunk
               uint32_t v[HW];
               tmem_ld<HW>(t_lane + col0, v);
               tmem_ld_wait();
-              uint32_t pk[HW / 2];
+              uint32_t pk[HW / 2];                         // bias is already in the accumulator
 #pragma unroll
-              for (int q = 0; q < HW / 8; ++q) {
-                const float4 b0 = *reinterpret_cast<const float4*>(bl + col0 + q * 8);
-                const float4 b1 = *reinterpret_cast<const float4*>(bl + col0 + q * 8 + 4);
-                const float2 f0 = add2(v[q * 8 + 0], v[q * 8 + 1], make_float2(b0.x, b0.y));
-                const float2 f1 = add2(v[q * 8 + 2], v[q * 8 + 3], make_float2(b0.z, b0.w));
-                const float2 f2 = add2(v[q * 8 + 4], v[q * 8 + 5], make_float2(b1.x, b1.y));
-                const float2 f3 = add2(v[q * 8 + 6], v[q * 8 + 7], make_float2(b1.z, b1.w));
-                pk[q * 4 + 0] = pack_relu_bf16(f0.x, f0.y);
-                pk[q * 4 + 1] = pack_relu_bf16(f1.x, f1.y);
-                pk[q * 4 + 2] = pack_relu_bf16(f2.x, f2.y);
-                pk[q * 4 + 3] = pack_relu_bf16(f3.x, f3.y);
-              }
+              for (int q = 0; q < HW / 2; ++q)
+                pk[q] = pack_relu_bf16(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
               tmem_st<HW / 2>(t_a + col0 / 2, pk);          // K elements [col0, col0 + HW) of this row
             }
             TL(2 + l * 4);
@@ -750,7 +754,7 @@ bool rollout_tc_supported(int O, int A, int L, int U, int H) {
 
 static size_t tc_smem_bytes(int L, int ntiles, int q, int nparts) {
   size_t b = (size_t)kAtomBytes + (size_t)L * 2 * kAtomBytes;      // weights
-  b += (size_t)(L + 1) * 128 * sizeof(float);                      // biases
+  b += (size_t)(L + 1) * 4096 + 4096;                              // bias K-blocks + ones tile
   b += 128 * sizeof(float);                                        // scaler
   b += kParts * 64 * sizeof(float);                                // slice penalty table
   b += (size_t)ntiles * q * nparts * 128 * sizeof(float);          // partial minima exchange
