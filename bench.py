@@ -95,6 +95,12 @@ def time_cpu_planner(c, budget_s=20.0, max_plans=12):
     from simba_b200 import synthetic
     z, eps, zf = synthetic.make_draws(c['I'], 1, c['N'], c['H'], c['A'], c['P'], c['O'], seed=2)
     pl = helpers.oracle_planner(c, 'penalty')
+    try:
+        # torchrun exports OMP_NUM_THREADS=1; the CPU planner is allowed every host thread it can use
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     pl.do_generate_action(c['state'], z[:, 0], eps[:, 0], zf[0])          # warm-up (BLAS threads, pages)
     times, t_start = [], time.perf_counter()
     while len(times) < max_plans and (time.perf_counter() - t_start < budget_s or len(times) < 2):
@@ -271,7 +277,10 @@ def main():
     ms_plan = ms.mean()
     roofline = {"kernel": "rollout_tc_kernel" if precision == 'bf16' else "rollout_f32_kernel",
                 "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one rollout_tc_kernel launch at this shape from
+                # the committed ncu --set full capture (profiles/r01_v4_c1_rollout_tc.txt): weights + actions
+                # are read once, outputs stay in L2 -> nowhere near HBM-bound
+                "frac": achieved_tf / peak_tf, "traffic": 841728 if precision == 'bf16' else None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PFLOP/s",
                 "flops_per_launch": flops_per_launch, "launch_ms": roll_ms,
                 "share_of_plan": c['I'] * roll_ms / ms_plan,
