@@ -148,7 +148,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
-    ap.add_argument('--extras', default=None, help="comma list of: c3, c4, fp32 (default: c3 when N > 1, c4 when N == 1)")
+    ap.add_argument('--extras', default=None, help="comma list of: c3, c4, fp32 (default: c3 when N > 1, c4,c3 when N == 1)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -302,7 +302,7 @@ def main():
     # ---- extras -----------------------------------------------------------------------------------
     extras = {}
     if args.extras is None:
-        args.extras = 'c3' if world > 1 else 'c4'
+        args.extras = 'c3' if world > 1 else 'c4,c3'
     want = [x for x in args.extras.split(',') if x]
     try:
         if 'fp32' in want and precision != 'fp32':
