@@ -473,6 +473,7 @@ struct simba_planner {
         *pairs_all = nullptr, *mu = nullptr, *sigma = nullptr, *best_action = nullptr,
         *best_score = nullptr, *scores = nullptr;
   uint64_t* row_cmask = nullptr;
+  unsigned long long* key_scratch = nullptr;
   int32_t *elite = nullptr, *active = nullptr, *iters = nullptr;
   // planning-call staging
   float *d_states = nullptr, *d_out_action = nullptr, *d_out_score = nullptr;
@@ -537,7 +538,7 @@ static void planner_free(simba_planner* p) {
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
   cudaFree(p->d_tiles); cudaFree(p->actions); cudaFree(p->row_ret); cudaFree(p->row_csum);
   cudaFree(p->pairs_local); cudaFree(p->pairs_all); cudaFree(p->mu); cudaFree(p->sigma);
-  cudaFree(p->best_action); cudaFree(p->best_score); cudaFree(p->scores); cudaFree(p->row_cmask);
+  cudaFree(p->best_action); cudaFree(p->best_score); cudaFree(p->scores); cudaFree(p->row_cmask); cudaFree(p->key_scratch);
   cudaFree(p->elite); cudaFree(p->active); cudaFree(p->iters); cudaFree(p->d_states);
   cudaFree(p->d_out_action); cudaFree(p->d_out_score); cudaFree(p->d_out_iters);
   cudaFree(p->d_seed);
@@ -631,6 +632,7 @@ extern "C" int simba_planner_create(simba_model_t* model, const simba_planner_co
   PL_ALLOC(p->best_action, S * A * 4);
   PL_ALLOC(p->best_score, S * 4);
   PL_ALLOC(p->scores, S * N * 4);
+  PL_ALLOC(p->key_scratch, S * N * 8);
   PL_ALLOC(p->elite, S * (size_t)cfg->n_elite * 4);
   PL_ALLOC(p->active, S * 4);
   PL_ALLOC(p->iters, S * 4);
@@ -789,6 +791,7 @@ static SelectParams make_select_params(simba_planner_t* p, const float* pairs_al
   sp.S = p->cfg.n_states; sp.N = p->cfg.n_samples; sp.N_local = p->geom.N_local;
   sp.K = p->cfg.n_elite; sp.H = p->cfg.horizon; sp.A = p->model->cfg.act_dim;
   sp.objective = p->cfg.objective; sp.c_max = (float)p->c_max;
+  sp.key_scratch = p->key_scratch;
   sp.pairs_all = pairs_all; sp.actions = actions; sp.active = active; sp.out_elite = out_elite;
   sp.out_scores = out_scores; sp.best_action = best_action; sp.best_score = best_score;
   return sp;

@@ -211,23 +211,78 @@ __global__ void __launch_bounds__(kSelectThreads) select_elites_kernel(SelectPar
     return pair_key(p.objective, pr.x, pr.y, p.c_max);
   };
 
-  // ---- MSD radix select of the K-th largest key ----------------------------------------------
+  // ---- stage the 64-bit order keys once (L2-resident scratch) and find their range --------------
+  __shared__ unsigned long long sh_kmin, sh_kmax;
+  if (tid == 0) { sh_best_key = 0ull; sh_best_idx = 0x7fffffff; sh_kmin = ~0ull; sh_kmax = 0ull; }
+  __syncthreads();
+  unsigned long long* keys = p.key_scratch + (long)s * N;
+  {
+    unsigned long long kmin = ~0ull, kmax = 0ull;
+    for (int base = 0; base < N; base += 4 * kSelectThreads) {
+      float2 pr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * kSelectThreads + tid;
+        pr[u] = i < N ? load_pair(i) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * kSelectThreads + tid;
+        if (i < N) {
+          const unsigned long long k = pair_key(p.objective, pr[u].x, pr[u].y, p.c_max);
+          keys[i] = k;
+          kmin = k < kmin ? k : kmin;
+          kmax = k > kmax ? k : kmax;
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long a = __shfl_xor_sync(0xffffffffu, kmin, d), c = __shfl_xor_sync(0xffffffffu, kmax, d);
+      kmin = a < kmin ? a : kmin;
+      kmax = c > kmax ? c : kmax;
+    }
+    if ((tid & 31) == 0) { atomicMin(&sh_kmin, kmin); atomicMax(&sh_kmax, kmax); }
+  }
+  __syncthreads();                                         // also publishes keys[] to the whole CTA
+  const unsigned long long kmin = sh_kmin, span = sh_kmax - sh_kmin;
+
+  // ---- MSD radix select of the K-th largest key on (key - kmin): the digits of the normalised keys
+  //      are spread over the bins (scores of one population share their exponent bits), and passes
+  //      above the span's top byte are skipped. Histogram updates are warp-aggregated
+  //      (__match_any_sync) so that heavy ties cost one shared-memory atomic per warp, not 32.
   uint64_t prefix = 0ull, mask = 0ull;
   int need = K;
-  const int top_byte = (p.objective == SIMBA_OBJ_FEASIBLE_FIRST) ? 7 : 3;
-  if (tid == 0) { sh_best_key = 0ull; sh_best_idx = 0x7fffffff; }
+  int top_byte = 7;
+  while (top_byte > 0 && ((span >> (8 * top_byte)) & 0xffull) == 0ull) --top_byte;
+  const int lane = tid & 31;
   for (int byte = top_byte; byte >= 0; --byte) {
     if (tid < 256) hist[tid] = 0;
     __syncthreads();
     const int shift = 8 * byte;
-    for (int i = tid; i < N; i += kSelectThreads) {
-      const uint64_t k = key_of(i);
-      if ((k & mask) == prefix) atomicAdd(&hist[(int)((k >> shift) & 0xffull)], 1);
+    for (int base = 0; base < N; base += 8 * kSelectThreads) {
+      uint64_t kk[8];                                       // 8 independent L2 loads in flight per thread
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * kSelectThreads + tid;
+        kk[u] = i < N ? keys[i] : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * kSelectThreads + tid;
+        int bin = -1;
+        if (i < N) {
+          const uint64_t k = kk[u] - kmin;
+          if ((k & mask) == prefix) bin = (int)((k >> shift) & 0xffull);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+      }
     }
     __syncthreads();
     if (tid < 256) {
       int above = 0;
-      for (int b = tid + 1; b < 256; ++b) above += hist[b];
+      for (int bb = tid + 1; bb < 256; ++bb) above += hist[bb];
       if (above < need && need <= above + hist[tid]) { sh_digit = tid; sh_need = need - above; }
     }
     __syncthreads();
@@ -236,30 +291,26 @@ __global__ void __launch_bounds__(kSelectThreads) select_elites_kernel(SelectPar
     need = sh_need;
     __syncthreads();
   }
-  const uint64_t T = prefix;   // K-th largest key; `need` of the keys == T are taken, lowest index first
+  const uint64_t T = prefix + kmin;   // K-th largest key; `need` of the keys == T are taken, lowest index first
 
   // ---- ordered compaction: each thread owns a contiguous index range -------------------------
   const int V = (N + kSelectThreads - 1) / kSelectThreads;
   const int lo = min(N, tid * V), hi = min(N, lo + V);
-  int eq_local = 0;
+  int eq_local = 0, gt_local = 0;
   uint64_t best_k = 0ull;
   int best_i = 0x7fffffff;
   for (int i = lo; i < hi; ++i) {
-    const uint64_t k = key_of(i);
+    const uint64_t k = keys[i];
     eq_local += (k == T);
+    gt_local += (k > T);
     if (k > best_k || best_i == 0x7fffffff) { best_k = k; best_i = i; }   // first max in range
   }
   const int eq_before = block_exclusive_scan<kSelectThreads>(eq_local, warp_sums, &sh_total);
-  int sel_local = 0, eq_run = eq_before;
+  const int eq_take = max(0, min(eq_local, need - eq_before));           // ties taken from this range
+  int pos = block_exclusive_scan<kSelectThreads>(gt_local + eq_take, warp_sums, &sh_total);
+  int eq_run = eq_before;
   for (int i = lo; i < hi; ++i) {
-    const uint64_t k = key_of(i);
-    if (k > T) ++sel_local;
-    else if (k == T) { if (eq_run < need) ++sel_local; ++eq_run; }
-  }
-  int pos = block_exclusive_scan<kSelectThreads>(sel_local, warp_sums, &sh_total);
-  eq_run = eq_before;
-  for (int i = lo; i < hi; ++i) {
-    const uint64_t k = key_of(i);
+    const uint64_t k = keys[i];
     bool sel = k > T;
     if (k == T) { sel = eq_run < need; ++eq_run; }
     if (sel) p.out_elite[(long)s * K + pos++] = i;
@@ -315,7 +366,19 @@ __device__ __forceinline__ void refit_body(const RefitParams& p, int s, const in
     if (grp < groups) {
       float acc = 0.0f;
       const float m = pass ? mean[c] : 0.0f;
-      for (int k = grp; k < p.K; k += groups) {
+      // gathers are independent: issue 8 at a time, accumulate in index order (deterministic)
+      int k = grp;
+      for (; k + 7 * groups < p.K; k += 8 * groups) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = acts[(long)elite[k + u * groups] * HA + c];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (pass) { const float d = __fsub_rn(v[u], m); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
+          else acc = __fadd_rn(acc, v[u]);
+        }
+      }
+      for (; k < p.K; k += groups) {
         const float v = acts[(long)elite[k] * HA + c];
         if (pass) { const float d = __fsub_rn(v, m); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
         else acc = __fadd_rn(acc, v);

@@ -32,6 +32,7 @@ struct SelectParams {                 // cem_mpc.py:56-60
   const float* pairs_all;             // [world, S, N_local, 2]
   const float* actions;               // [S, N, H, A]
   const int32_t* active;
+  unsigned long long* key_scratch;    // [S, N] staged order keys (planner workspace)
   int32_t* out_elite;                 // [S, K]
   float* out_scores;                  // [S, N] or null
   float* best_action;                 // [S, A]
