@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "cem_kernels.cuh"
+#include "internal.h"
 #include "rollout_params.cuh"
 
 using namespace simba;
@@ -22,6 +23,16 @@ using namespace simba;
 static thread_local std::string g_last_error;
 
 static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+int simba::set_error(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -151,6 +162,22 @@ extern "C" int simba_model_set_layer(simba_model_t* m, int32_t member, int32_t l
   m->committed = false;
   return SIMBA_OK;
 }
+
+extern "C" int simba_model_get_layer(simba_model_t* m, int32_t member, int32_t layer,
+                                     float* kernel_out, float* bias_out) {
+  if (!m || !kernel_out || !bias_out) return fail(SIMBA_ERR_BAD_CONFIG, "null argument");
+  const int L = m->cfg.n_layers;
+  if (member < 0 || member >= m->cfg.ensemble_size || layer < 0 || layer >= L + 2)
+    return fail(SIMBA_ERR_BAD_CONFIG, "member %d / layer %d out of range", member, layer);
+  const int idx = member * (L + 2) + layer;
+  if (!m->layer_set[idx])
+    return fail(SIMBA_ERR_NOT_READY, "member %d layer %d has no weights", member, layer);
+  memcpy(kernel_out, m->kernels[idx].data(), m->kernels[idx].size() * sizeof(float));
+  memcpy(bias_out, m->biases[idx].data(), m->biases[idx].size() * sizeof(float));
+  return SIMBA_OK;
+}
+
+const simba_model_config_t* simba::model_config(const simba_model_t* m) { return &m->cfg; }
 
 extern "C" int simba_model_set_scaler(simba_model_t* m, const float* mn, const float* mx,
                                       int32_t scale_features) {

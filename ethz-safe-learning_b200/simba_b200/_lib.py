@@ -58,7 +58,16 @@ class PlannerConfig(C.Structure):
                 ('scorer', Scorer)]
 
 
+class TrainerConfig(C.Structure):
+    _fields_ = [('batch_size', C.c_int32), ('max_eval_rows', C.c_int32),
+                ('learning_rate', C.c_float), ('lr_schedule', C.c_int32),
+                ('steps_per_epoch', C.c_int32), ('train_epochs', C.c_int32),
+                ('beta1', C.c_float), ('beta2', C.c_float), ('epsilon', C.c_float),
+                ('clipvalue', C.c_float)]
+
+
 _vp, _i32, _u64, _f = C.c_void_p, C.c_int32, C.c_uint64, C.c_float
+_i64 = C.c_int64
 _P = C.POINTER
 
 # name -> argtypes (every function returns int unless listed in _RESTYPES)
@@ -91,13 +100,24 @@ _SIGNATURES = {
     'simba_scale': [_vp, _vp, _i32, _vp, _vp],
     'simba_score_trajectories': [_vp, _vp, _vp, _vp, _vp],
     'simba_scorer_eval': [_P(Scorer), _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
+    'simba_trainer_create': [_vp, _P(TrainerConfig), _P(_vp)],
+    'simba_trainer_destroy': [_vp],
+    'simba_trainer_step': [_vp, _vp, _vp, _i32, _vp, _vp],
+    'simba_trainer_fit': [_vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp],
+    'simba_trainer_validation': [_vp, _vp, _vp, _i64, _vp, _vp],
+    'simba_trainer_sync_model': [_vp, _vp],
+    'simba_trainer_get': [_vp, _i32, _i32, _i32, _vp, _vp],
+    'simba_trainer_iterations': [_vp],
+    'simba_trainer_launches_per_step': [_vp],
+    'simba_model_get_layer': [_vp, _i32, _i32, _vp, _vp],
     'simba_philox_raw': [_P(C.c_uint32 * 4), _P(C.c_uint32 * 2), _P(C.c_uint32 * 4)],
     'simba_philox_normals': [_u64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp],
     'simba_last_error': [],
     'simba_version': [],
     'simba_device_check': [],
 }
-_RESTYPES = {'simba_last_error': C.c_char_p, 'simba_version': C.c_char_p}
+_RESTYPES = {'simba_last_error': C.c_char_p, 'simba_version': C.c_char_p,
+             'simba_trainer_iterations': C.c_int64}
 
 LIB_PATH = pathlib.Path(__file__).resolve().parent / 'libsimba_b200.so'
 _lib = None

@@ -1,9 +1,9 @@
 """TransitionModel — mirrors simba/models/transition_model.py for the inference methods.
 
 `unfold_sequences` (transition_model.py:64-77), `scale` (:79-87), `predict` (:52-56) and
-`simulate_trajectories` (:58-62) run on the GPU through libsimba_b200.so. `fit` trains the
-ensemble in the reference (:34-40) and is out of scope; `_fit_statistics` (:42-50), which produces
-the scaler bounds the planner needs, is implemented.
+`simulate_trajectories` (:58-62) run on the GPU through libsimba_b200.so. `fit` (:34-40) fits the
+scaler statistics (`_fit_statistics`, :42-50) and trains the ensemble on scaled inputs and
+observation deltas with the device trainer (MlpEnsemble.fit).
 """
 import numpy as np
 import torch
@@ -68,8 +68,12 @@ class TransitionModel(BaseModel):
                             np.where(np.isfinite(high), high, inputs.max(axis=0)))
 
     def fit(self, inputs, targets):
-        self._fit_statistics(np.asarray(inputs))
-        return self.model.fit(inputs, targets)
+        """transition_model.py:34-40."""
+        inputs = np.asarray(inputs, dtype=np.float32)
+        self._fit_statistics(inputs)
+        observations = inputs[:, :self.observation_space_dim]
+        next_observations = np.asarray(targets, dtype=np.float32)
+        return self.model.fit(self.scale(inputs), (next_observations - observations).astype(np.float32))
 
     def predict(self, inputs):
         """transition_model.py:52-56 -> np[B, 2, O]."""

@@ -246,6 +246,57 @@ int simba_scorer_eval(const simba_scorer_t* sc, const float* obs, const float* n
                       int32_t batch, int32_t obs_dim, float* out_reward, int32_t* out_done,
                       float* out_cost, void* stream);
 
+/* ---- ensemble training step ----------------------------------------
+ * Replaces MlpEnsemble.training_step / validation_step / fit (simba/models/mlp_ensemble.py:134-187):
+ * forward (training=True, dropout 0), negative_log_likelihood (:64-67) summed over members / E,
+ * backward, and tf.keras.optimizers.Adam(clipvalue, epsilon) with EpochLearningRateSchedule
+ * (:70-88, :113-117) — all fp32 CUDA kernels on master weights that stay on the device. */
+typedef struct simba_trainer simba_trainer_t;
+typedef struct simba_trainer_config {
+  int32_t batch_size;        /* models.yaml:4 — the largest training batch (rows per member)     */
+  int32_t max_eval_rows;     /* row capacity of validation_step chunks (>= batch_size)          */
+  float learning_rate;       /* models.yaml:6                                                   */
+  int32_t lr_schedule;       /* models.yaml:7: 1 = EpochLearningRateSchedule                    */
+  int32_t steps_per_epoch;   /* mlp_ensemble.py:114 (training_steps)                            */
+  int32_t train_epochs;      /* agent_factory.py:22                                             */
+  float beta1, beta2;        /* Keras defaults 0.9, 0.999                                       */
+  float epsilon;             /* mlp_ensemble.py:117 (1e-5)                                      */
+  float clipvalue;           /* mlp_ensemble.py:116 (1.0); <= 0 disables clipping               */
+} simba_trainer_config_t;
+
+/* Copies the model's current (set_layer) weights as fp32 master weights; Adam state zeroed. */
+int simba_trainer_create(simba_model_t* m, const simba_trainer_config_t* cfg, simba_trainer_t** out);
+int simba_trainer_destroy(simba_trainer_t* t);
+/* MlpEnsemble.training_step — mlp_ensemble.py:134-146. x DEVICE [E, rows, O+A] (already scaled),
+ * y DEVICE [E, rows, O], rows <= batch_size; out_loss DEVICE [1] (may be NULL). Async on stream. */
+int simba_trainer_step(simba_trainer_t* t, const float* x, const float* y, int32_t rows,
+                       float* out_loss, void* stream);
+/* The inner loop of MlpEnsemble.fit — mlp_ensemble.py:172-186: `steps` training steps, step s on
+ * rows batch_index[s, e, 0:batch_rows[s]] of inputs/targets for member e. inputs DEVICE [n, O+A],
+ * targets DEVICE [n, O], batch_index DEVICE int32 [steps, E, batch_size], batch_rows DEVICE int32
+ * [steps] or NULL (= batch_size everywhere), out_losses DEVICE [steps]. One CUDA graph per step. */
+int simba_trainer_fit(simba_trainer_t* t, const float* inputs, const float* targets, int64_t n,
+                      const int32_t* batch_index, const int32_t* batch_rows, int32_t steps,
+                      float* out_losses, void* stream);
+/* MlpEnsemble.validation_step — mlp_ensemble.py:148-156: every member on the same rows.
+ * x DEVICE [rows, O+A], y DEVICE [rows, O]; out_loss DEVICE [1]. */
+int simba_trainer_validation(simba_trainer_t* t, const float* x, const float* y, int64_t rows,
+                             float* out_loss, void* stream);
+/* Hands the trained weights to the model handle (set_layer + commit, bumps its generation so
+ * planners re-capture). Synchronises the stream. */
+int simba_trainer_sync_model(simba_trainer_t* t, void* stream);
+/* which: 0 weights, 1 last gradients (before clipping), 2 Adam m, 3 Adam v. Keras layout
+ * (kernel [in, out], bias [out]) of `layer` in [0, L+2) as in simba_model_set_layer. HOST out. */
+int simba_trainer_get(simba_trainer_t* t, int32_t which, int32_t member, int32_t layer,
+                      float* kernel_out, float* bias_out);
+/* optimizer.iterations */
+int64_t simba_trainer_iterations(simba_trainer_t* t);
+/* kernels launched by one training step (for bench.py's gpu_launches) */
+int simba_trainer_launches_per_step(simba_trainer_t* t);
+/* read back the weights given to simba_model_set_layer. HOST out. */
+int simba_model_get_layer(simba_model_t* m, int32_t member, int32_t layer, float* kernel_out,
+                          float* bias_out);
+
 /* ---- RNG contract probes (tests) --------------------------------------------------------- */
 /* raw Philox4x32-10 block: HOST in/out, computed ON THE DEVICE (no CPU path). */
 int simba_philox_raw(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);

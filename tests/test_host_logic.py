@@ -1,7 +1,9 @@
 """Host-side mirror of the reference interface (no GPU needed)."""
 import numpy as np
+import torch
 import pytest
 
+from simba_b200 import _lib
 from tests import helpers
 
 
@@ -95,12 +97,13 @@ def test_planner_config_is_filled_from_policy_kwargs():
     assert (cfg.prior_mu, abs(cfg.prior_sigma - 0.27) < 1e-7) == (0.5, True)
 
 
-def test_fit_is_out_of_scope_but_statistics_work():
+def test_fit_has_no_cpu_path_but_statistics_work():
     c = helpers.workload('tiny')
     pol = helpers.cuda_policy(c, 'reward')
     tm = pol.model
-    with pytest.raises(NotImplementedError):
-        tm.model.fit(np.zeros((4, 62), np.float32), np.zeros((4, 60), np.float32))
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.SimbaError):          # training is CUDA-only, like planning
+            tm.model.fit(np.zeros((4, 62), np.float32), np.zeros((4, 60), np.float32))
     from simba_b200.environment_utils import ScorerEnvironment
     from simba_b200.models import TransitionModel
     env = ScorerEnvironment()
