@@ -148,7 +148,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
-    ap.add_argument('--extras', default=None, help="comma list of: c3, c4, fp32 (default: c3 when N > 1, c4,c3 when N == 1)")
+    ap.add_argument('--extras', default=None, help="comma list of: c3, c4, fp32, train (default: c3 when N > 1, c4,c3,train when N == 1)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -302,7 +302,7 @@ def main():
     # ---- extras -----------------------------------------------------------------------------------
     extras = {}
     if args.extras is None:
-        args.extras = 'c3' if world > 1 else 'c4,c3'
+        args.extras = 'c3' if world > 1 else 'c4,c3,train'
     want = [x for x in args.extras.split(',') if x]
     try:
         if 'fp32' in want and precision != 'fp32':
@@ -311,6 +311,8 @@ def main():
             extras['c4'] = bench_batched(synthetic, torch, precision, flush, world, rank)
         if 'c3' in want:
             extras['c3'] = bench_c3(synthetic, torch, dist, lib, _lib, precision, world, rank)
+        if 'train' in want and rank == 0:
+            extras['train'] = bench_train(torch, cpu=not args.no_cpu_baseline and world == 1)
     except Exception as e:                      # extras never take the headline line down
         extras['error'] = repr(e)
     if extras:
@@ -347,6 +349,60 @@ def bench_plain(synthetic, torch, c, precision, states, flush, K):
     torch.cuda.synchronize()
     ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     return {"plans_per_s": 1e3 / ms, "ms_per_plan": ms, "precision": precision}
+
+
+def bench_train(torch, cpu=True, steps=1000, rows=24000):
+    """MlpEnsemble training steps (E=5 members x batch 64, 62 -> 4x128 ->
+    2x60, Adam) through simba_trainer_fit with the data and the batch schedule resident in HBM;
+    beside it the numpy training oracle on the host cores."""
+    from simba_b200 import _device, _lib
+    from simba_b200.models import MlpEnsemble
+    import ctypes as C
+    E, B, IN, O = 5, 64, 62, 60
+    rng = np.random.default_rng(0)
+    ens = MlpEnsemble(IN, O, E, batch_size=B, training_steps=5000, mlp_params=dict(n_layers=4, units=128))
+    x = rng.uniform(0, 1, (rows, IN)).astype(np.float32)
+    y = rng.normal(0, 0.1, (rows, O)).astype(np.float32)
+    index, _ = ens.batch_schedule(rows, steps)
+    t = ens._ensure_trainer()
+    dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    dindex = torch.from_numpy(index).cuda()
+    losses = torch.empty(steps, device='cuda')
+
+    def run(n):
+        _lib.check(ens._lib.simba_trainer_fit(t, _device.ptr(dx), _device.ptr(dy), rows, _device.ptr(dindex),
+                                              C.c_void_p(0), n, _device.ptr(losses), _device.stream_ptr()))
+    run(20)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    run(steps)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    ens._trained_ahead = True
+    per_step = int(ens._lib.simba_trainer_launches_per_step(t)) + 1          # + the batch gather
+    out = {"workload": "E=%d x batch %d, 62->4x128->2x60, Adam(clipvalue 1, eps 1e-5); %d steps, data in HBM" % (E, B, steps),
+           "steps_per_s": steps / (ms * 1e-3), "us_per_step": ms * 1e3 / steps, "launches_per_step": per_step,
+           "loss_first": float(losses[0]), "loss_last": float(losses[steps - 1])}
+    if cpu:
+        from oracle import train_oracle as T           # CPU baseline leg only
+        try:
+            import threadpoolctl
+            threadpoolctl.threadpool_limits(limits=os.cpu_count())
+        except Exception:
+            pass
+        ora = T.EnsembleTrainer([m.get_weights() for m in MlpEnsemble(IN, O, E, mlp_params=dict(n_layers=4, units=128)).ensemble],
+                                batch_size=B)
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < 5.0:
+            idx = index[n % steps]
+            ora.training_step(x[idx], y[idx])
+            n += 1
+        dt = time.perf_counter() - t0
+        out["cpu_port_steps_per_s"] = n / dt
+        out["cpu_sample"] = "%d numpy fp32 training steps in %.1f s (all host cores available to BLAS)" % (n, dt)
+    return out
 
 
 def bench_batched(synthetic, torch, precision, flush, world, rank, S=1024):

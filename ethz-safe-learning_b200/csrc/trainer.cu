@@ -6,15 +6,18 @@
 // Shape of the work: E members x batch 64 x a 4x128 MLP is 28 MFLOP per member-step, far below
 // what one launch can hide, so the step is latency-bound. The design goal is therefore few, wide
 // launches that stay inside one CUDA graph:
-//   forward   L+1 launches   Y = act([X, 1] . theta_l)            grid (N/32, rows/64, E)
-//   nll       1 launch       loss, d(mu), d(raw var), lr_t         grid (rows/64, E)
-//   backward  L launches     dZ_{l-1} = relu'(H) * (dZ_l . W_l^T)  grid (K/32, rows/64, E)
+//   forward   L launches     H_l = relu([H_{l-1}, 1] . theta_l)    grid (N/32, rows/16, E)
+//   head+nll  1 launch       mu, var, loss, d(mu), d(raw var), lr_t (mu / var stay in registers)
+//   backward  L launches     dZ_{l-1} = relu'(H) * (dZ_l . W_l^T)  grid (K/32, rows/16, E)
 //   update    1 launch       dtheta = [H, 1]^T . dZ for EVERY layer, clip, Adam, in one grid
+// i.e. 2L + 2 launches per step; fit()'s batch gather is folded into the kernels that read the
+// batch. Every CTA stages its whole (<= 128-deep) contraction with one wave of loads, so it pays
+// the memory latency once, and the tiles are small so that one layer spreads over ~80 SMs.
 // Parameters of train layer l are stored as one [(K_l + 1) x N_l] row-major block (Keras kernel
 // [in, out] followed by the bias row), so "bias" is just the row that multiplies the constant 1
 // and the weight-gradient GEMM produces the bias gradient as its last row. The Gaussian head's
-// two Dense layers (mlp_ensemble.py:28-30) are one block with N = 2 * O (mu columns, then var).
-// Reductions are in a fixed order: results are bit-reproducible run to run.
+// two Dense layers (mlp_ensemble.py:28-30) are one block with N = 2 * O whose columns interleave
+// (mu_0, var_0, mu_1, var_1, ...). Reductions are in a fixed order: results are bit-reproducible.
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -26,10 +29,13 @@ using namespace simba;
 
 namespace {
 
-constexpr int kTileM = 64;     // rows per CTA in forward / backward
+constexpr int kRowsF = 16;     // rows per CTA in forward / backward (more, smaller CTAs: the step is
+                               // latency-bound, so the work is spread over as many SMs as possible)
 constexpr int kTileN = 32;     // output columns per CTA
-constexpr int kTileK = 32;     // contraction chunk staged in shared memory
-constexpr int kThreads = 256;
+constexpr int kChunk = 128;    // contraction chunk staged in shared memory in ONE load phase
+constexpr int kThreadsF = 128;
+constexpr int kRowsU = 64;     // batch rows per chunk in the weight-gradient kernel
+constexpr int kThreadsU = 256;
 
 struct TrainState {
   int iterations;        // optimizer.iterations
@@ -59,29 +65,16 @@ __device__ __forceinline__ int resolve_rows(const FitDesc* desc, const TrainStat
   return rows_fixed;
 }
 
-// ---------------------------------------------------------------------------------------------
-// fit(): batch gather (mlp_ensemble.py:175-176 `train_inputs[shuffles_per_mlp]`)
-// ---------------------------------------------------------------------------------------------
+// fit(): `train_inputs[shuffles_per_mlp]` (mlp_ensemble.py:175-176) is never materialised — the
+// kernels that read the batch follow the index
+__device__ __forceinline__ const int* batch_rows_of(const FitDesc* desc, const TrainState* st, int e,
+                                                    int ensemble) {
+  return desc->batch_index + ((int64_t)st->fit_step * ensemble + e) * desc->bmax;
+}
+
 __global__ void set_fit_desc_kernel(FitDesc d, FitDesc* out, TrainState* st) {
   *out = d;
   st->fit_step = 0;
-}
-
-__global__ void gather_batch_kernel(const FitDesc* desc, const TrainState* st, int rows_fixed,
-                                    int in_dim, int out_dim, float* x, float* y,
-                                    int64_t x_estride, int64_t y_estride) {
-  const int rows = resolve_rows(desc, st, rows_fixed);
-  const int e = blockIdx.y;
-  const int width = in_dim + out_dim;
-  const int* idx = desc->batch_index + ((int64_t)st->fit_step * gridDim.y + e) * desc->bmax;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * width; i += gridDim.x * blockDim.x) {
-    const int r = i / width, c = i - r * width;
-    const int64_t src = idx[r];
-    if (c < in_dim)
-      x[e * x_estride + (int64_t)r * in_dim + c] = desc->inputs[src * in_dim + c];
-    else
-      y[e * y_estride + (int64_t)r * out_dim + (c - in_dim)] = desc->targets[src * out_dim + (c - in_dim)];
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -90,6 +83,7 @@ __global__ void gather_batch_kernel(const FitDesc* desc, const TrainState* st, i
 struct LayerArgs {
   const float* in;        // [E][rows][K]   (e-stride may be 0: validation shares its rows)
   int64_t in_estride;
+  int gather_in;          // 1: rows of `in` are desc->inputs[batch_index[...]] (layer 0 inside fit)
   const float* theta;     // [E][pn]
   int64_t pn;
   int off, K, N;
@@ -97,77 +91,118 @@ struct LayerArgs {
   int64_t out_estride;
   const float* dz;        // backward only: dZ_l [E][rows][N]
   int64_t dz_estride;
-  int relu;
+  int ensemble;
 };
 
-__global__ void __launch_bounds__(kThreads)
-train_forward_kernel(LayerArgs a, const FitDesc* desc, const TrainState* st, int rows_fixed) {
-  const int rows = resolve_rows(desc, st, rows_fixed);
-  const int e = blockIdx.z, r0 = blockIdx.y * kTileM, n0 = blockIdx.x * kTileN;
-  if (r0 >= rows) return;
-  __shared__ float Xs[kTileM][kTileK + 1];
-  __shared__ __align__(16) float Ws[kTileK][kTileN];
-  const float* X = a.in + e * a.in_estride;
+// acc[j] = sum_k X[r0 + ty][k] * W[k][n0 + tx * 4 + j]; all of a <= 128-deep contraction is staged
+// by one wave of loads, so a CTA pays the memory latency once
+__device__ __forceinline__ void forward_tile(const LayerArgs& a, const FitDesc* desc,
+                                             const TrainState* st, int rows, int e, int r0, int n0,
+                                             float (&Xs)[kRowsF][kChunk + 1],
+                                             float (&Ws)[kChunk][kTileN], float (&acc)[4]) {
   const float* W = a.theta + e * a.pn + a.off;
   const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
-  float acc[2][4] = {};
-  for (int k0 = 0; k0 < a.K; k0 += kTileK) {
-    for (int i = tid; i < kTileM * kTileK; i += kThreads) {
-      const int r = i >> 5, k = i & 31;
-      Xs[r][k] = (r0 + r < rows && k0 + k < a.K) ? X[(int64_t)(r0 + r) * a.K + k0 + k] : 0.0f;
+  const float* X = a.in + e * a.in_estride;
+  const int* gidx = a.gather_in ? batch_rows_of(desc, st, e, a.ensemble) : nullptr;
+  const bool vec = (a.N & 3) == 0;      // then every block offset and row of W is 16-byte aligned
+  for (int k0 = 0; k0 < a.K; k0 += kChunk) {
+    const int kc = min(kChunk, a.K - k0);
+    if (k0) __syncthreads();
+    // all global loads of the chunk are issued into registers before the first shared store, so
+    // the CTA waits for memory once (the step is latency-bound, not bandwidth-bound)
+    float xv[kRowsF * kChunk / kThreadsF];
+#pragma unroll
+    for (int j = 0; j < kRowsF * kChunk / kThreadsF; ++j) {
+      const int i = tid + j * kThreadsF, r = i >> 7, k = i & (kChunk - 1);
+      xv[j] = 0.0f;
+      if (r0 + r < rows && k < kc) {
+        const float* row = gidx ? desc->inputs + (int64_t)gidx[r0 + r] * a.K : X + (int64_t)(r0 + r) * a.K;
+        xv[j] = __ldg(row + k0 + k);
+      }
     }
-    for (int i = tid; i < kTileK * kTileN; i += kThreads) {
-      const int k = i >> 5, n = i & 31;
-      Ws[k][n] = (k0 + k < a.K && n0 + n < a.N) ? W[(int64_t)(k0 + k) * a.N + n0 + n] : 0.0f;
+    if (vec) {
+      float4 wv[kChunk * kTileN / 4 / kThreadsF];
+#pragma unroll
+      for (int j = 0; j < kChunk * kTileN / 4 / kThreadsF; ++j) {
+        const int i = tid + j * kThreadsF, k = i >> 3, n = (i & 7) * 4;
+        wv[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (k < kc && n0 + n < a.N)
+          wv[j] = __ldcg(reinterpret_cast<const float4*>(W + (int64_t)(k0 + k) * a.N + n0 + n));
+      }
+#pragma unroll
+      for (int j = 0; j < kChunk * kTileN / 4 / kThreadsF; ++j) {
+        const int i = tid + j * kThreadsF;
+        *reinterpret_cast<float4*>(&Ws[i >> 3][(i & 7) * 4]) = wv[j];
+      }
+    } else {
+      float wv[kChunk * kTileN / kThreadsF];
+#pragma unroll
+      for (int j = 0; j < kChunk * kTileN / kThreadsF; ++j) {
+        const int i = tid + j * kThreadsF, k = i >> 5, n = i & 31;
+        wv[j] = (k < kc && n0 + n < a.N) ? __ldcg(W + (int64_t)(k0 + k) * a.N + n0 + n) : 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < kChunk * kTileN / kThreadsF; ++j) {
+        const int i = tid + j * kThreadsF;
+        Ws[i >> 5][i & 31] = wv[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kRowsF * kChunk / kThreadsF; ++j) {
+      const int i = tid + j * kThreadsF;
+      Xs[i >> 7][i & (kChunk - 1)] = xv[j];
     }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kTileK; ++k) {
-      const float x0 = Xs[ty * 2][k], x1 = Xs[ty * 2 + 1][k];
+#pragma unroll 8
+    for (int k = 0; k < kc; ++k) {
+      const float x = Xs[ty][k];
       const float4 w = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
-      acc[0][0] = fmaf(x0, w.x, acc[0][0]); acc[0][1] = fmaf(x0, w.y, acc[0][1]);
-      acc[0][2] = fmaf(x0, w.z, acc[0][2]); acc[0][3] = fmaf(x0, w.w, acc[0][3]);
-      acc[1][0] = fmaf(x1, w.x, acc[1][0]); acc[1][1] = fmaf(x1, w.y, acc[1][1]);
-      acc[1][2] = fmaf(x1, w.z, acc[1][2]); acc[1][3] = fmaf(x1, w.w, acc[1][3]);
-    }
-    __syncthreads();
-  }
-  const float* bias = W + (int64_t)a.K * a.N;
-  float* Y = a.out + e * a.out_estride;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int r = r0 + ty * 2 + i;
-    if (r >= rows) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n >= a.N) continue;
-      float v = acc[i][j] + bias[n];
-      if (a.relu) v = fmaxf(v, 0.0f);
-      Y[(int64_t)r * a.N + n] = v;
+      acc[0] = fmaf(x, w.x, acc[0]); acc[1] = fmaf(x, w.y, acc[1]);
+      acc[2] = fmaf(x, w.z, acc[2]); acc[3] = fmaf(x, w.w, acc[3]);
     }
   }
 }
 
+__global__ void __launch_bounds__(kThreadsF)
+train_forward_kernel(LayerArgs a, const FitDesc* desc, const TrainState* st, int rows_fixed) {
+  const int rows = resolve_rows(desc, st, rows_fixed);
+  const int e = blockIdx.z, r0 = blockIdx.y * kRowsF, n0 = blockIdx.x * kTileN;
+  if (r0 >= rows) return;
+  __shared__ float Xs[kRowsF][kChunk + 1];
+  __shared__ __align__(16) float Ws[kChunk][kTileN];
+  float acc[4] = {};
+  forward_tile(a, desc, st, rows, e, r0, n0, Xs, Ws, acc);
+  const int tx = threadIdx.x & 7, r = r0 + (threadIdx.x >> 3);
+  if (r >= rows) return;
+  const float* bias = a.theta + e * a.pn + a.off + (int64_t)a.K * a.N;
+  float* Y = a.out + e * a.out_estride + (int64_t)r * a.N;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = n0 + tx * 4 + j;
+    if (n < a.N) Y[n] = fmaxf(acc[j] + bias[n], 0.0f);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
-// negative_log_likelihood (mlp_ensemble.py:64-67) and its gradient w.r.t. the head pre-activations
+// Gaussian head + negative_log_likelihood (mlp_ensemble.py:28-34, :64-67) + its gradient w.r.t.
+// the head pre-activations, fused: the head block stores (mu_o, var_o) in adjacent columns, so a
+// thread's four accumulators are two complete outputs and mu / var never go to memory.
 // ---------------------------------------------------------------------------------------------
 struct NllArgs {
-  const float* raw;        // [E][rows][2 O]: mu, then the var head's pre-activation
-  int64_t raw_estride;
-  const float* y;          // [E][rows][O]
+  const float* y;          // [E][rows][O] (ignored when gather_y)
   int64_t y_estride;
-  float* d_raw;            // [E][rows][2 O] or null (validation)
+  int gather_y;            // 1: rows of y are desc->targets[batch_index[...]]
+  float* d_raw;            // [E][rows][2 O] (interleaved like the head block) or null (validation)
   int64_t d_estride;
-  float* partial;          // [E][tiles][2]
+  float* partial;          // [E][tiles_cap][2]
   int tiles_cap;
-  int out_dim, ensemble;
+  int out_dim;
   int train;               // 1: last CTA finalises the loss and the step's lr_t
   float* out_loss;         // device [1] or null
 };
 
 __device__ __forceinline__ float block_sum(float v, float* scratch) {
-  // fixed-order tree: shuffles inside the warp, then warp 0 adds the 8 warp sums in order
+  // fixed-order tree: shuffles inside the warp, then thread 0 adds the warp sums in order
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -176,7 +211,7 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
   __syncthreads();
   float s = 0.0f;
   if (threadIdx.x == 0)
-    for (int i = 0; i < kThreads / 32; ++i) s += scratch[i];
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += scratch[i];
   return s;   // valid in thread 0
 }
 
@@ -186,68 +221,88 @@ __device__ float schedule_lr(const OptParams& o, int iterations) {
   return fmaxf(o.lr0 * (1.0f - epochs / (float)o.train_epochs), 0.0f);
 }
 
-__global__ void __launch_bounds__(kThreads)
-train_nll_kernel(NllArgs a, OptParams opt, const FitDesc* desc, TrainState* st, int rows_fixed) {
+__global__ void __launch_bounds__(kThreadsF)
+train_head_nll_kernel(LayerArgs a, NllArgs n, OptParams opt, const FitDesc* desc, TrainState* st,
+                      int rows_fixed) {
   const int rows = resolve_rows(desc, st, rows_fixed);
-  const int e = blockIdx.y, r0 = blockIdx.x * kTileM;
-  const int O = a.out_dim;
-  __shared__ float scratch[kThreads / 32];
+  const int e = blockIdx.z, r0 = blockIdx.y * kRowsF, n0 = blockIdx.x * kTileN;
+  const int O = n.out_dim;
+  __shared__ float Xs[kRowsF][kChunk + 1];
+  __shared__ __align__(16) float Ws[kChunk][kTileN];
+  __shared__ float scratch[kThreadsF / 32];
   __shared__ bool last;
   float s_log = 0.0f, s_sq = 0.0f;
   if (r0 < rows) {
-    const float c = 1.0f / ((float)rows * (float)O * (float)a.ensemble);
-    const int nr = min(kTileM, rows - r0);
-    const float* raw = a.raw + e * a.raw_estride + (int64_t)r0 * 2 * O;
-    const float* y = a.y + e * a.y_estride + (int64_t)r0 * O;
-    float* d = a.d_raw ? a.d_raw + e * a.d_estride + (int64_t)r0 * 2 * O : nullptr;
-    for (int i = threadIdx.x; i < nr * O; i += kThreads) {
-      const int r = i / O, o = i - r * O;
-      const float mu = raw[(int64_t)r * 2 * O + o];
-      const float pre = raw[(int64_t)r * 2 * O + O + o];
-      const float var = softplus_tf(pre) + 1e-4f;
-      const float diff = mu - y[(int64_t)r * O + o];
-      const float inv = 1.0f / var;
-      s_log += logf(6.28318530717958647692f * var);
-      s_sq += diff * diff * inv;
-      if (d) {
-        d[(int64_t)r * 2 * O + o] = c * diff * inv;
-        const float sig = 1.0f / (1.0f + expf(-pre));
-        d[(int64_t)r * 2 * O + O + o] = 0.5f * c * (inv - diff * diff * inv * inv) * sig;
+    float acc[4] = {};
+    forward_tile(a, desc, st, rows, e, r0, n0, Xs, Ws, acc);
+    const int tx = threadIdx.x & 7, r = r0 + (threadIdx.x >> 3);
+    if (r < rows) {
+      const float c = 1.0f / ((float)rows * (float)O * (float)a.ensemble);
+      const float* bias = a.theta + e * a.pn + a.off + (int64_t)a.K * a.N;
+      const float* y = n.gather_y
+          ? desc->targets + (int64_t)batch_rows_of(desc, st, e, a.ensemble)[r] * O
+          : n.y + e * n.y_estride + (int64_t)r * O;
+      float* d = n.d_raw ? n.d_raw + e * n.d_estride + (int64_t)r * 2 * O : nullptr;
+#pragma unroll
+      for (int j = 0; j < 4; j += 2) {
+        const int col = n0 + tx * 4 + j;
+        if (col >= a.N) continue;
+        const int o = col >> 1;
+        const float mu = acc[j] + bias[col];
+        const float pre = acc[j + 1] + bias[col + 1];
+        const float var = softplus_tf(pre) + 1e-4f;
+        const float diff = mu - y[o];
+        const float inv = 1.0f / var;
+        s_log += logf(6.28318530717958647692f * var);
+        s_sq += diff * diff * inv;
+        if (d) {
+          d[col] = c * diff * inv;
+          const float sig = 1.0f / (1.0f + expf(-pre));
+          d[col + 1] = 0.5f * c * (inv - diff * diff * inv * inv) * sig;
+        }
       }
     }
   }
   const float t_log = block_sum(s_log, scratch);
   const float t_sq = block_sum(s_sq, scratch);
+  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
   if (threadIdx.x == 0) {
-    a.partial[((int64_t)e * a.tiles_cap + blockIdx.x) * 2 + 0] = t_log;
-    a.partial[((int64_t)e * a.tiles_cap + blockIdx.x) * 2 + 1] = t_sq;
+    n.partial[((int64_t)e * n.tiles_cap + tile) * 2 + 0] = t_log;
+    n.partial[((int64_t)e * n.tiles_cap + tile) * 2 + 1] = t_sq;
   }
-  if (!a.train) return;
-  // the last CTA to arrive adds the partials in (member, tile) order and prepares the update
+  if (!n.train) return;
+  // the last CTA to arrive adds the partials in a fixed order and prepares the update
   if (threadIdx.x == 0) {
     __threadfence();
-    const unsigned total = gridDim.x * gridDim.y;
+    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
     last = (atomicAdd(&st->nll_ticket, 1u) == total - 1);
   }
   __syncthreads();
-  if (!last || threadIdx.x != 0) return;
+  if (!last || threadIdx.x >= 32) return;
   __threadfence();
-  const int tiles = (rows + kTileM - 1) / kTileM;
+  const int lane = threadIdx.x;
+  const int tiles = ((rows + kRowsF - 1) / kRowsF) * gridDim.x;
   const float denom = (float)rows * (float)O;
   float loss = 0.0f;
   for (int m = 0; m < a.ensemble; ++m) {
     float sl = 0.0f, sq = 0.0f;
-    for (int t = 0; t < tiles; ++t) {
-      sl += __ldcg(&a.partial[((int64_t)m * a.tiles_cap + t) * 2 + 0]);
-      sq += __ldcg(&a.partial[((int64_t)m * a.tiles_cap + t) * 2 + 1]);
+    for (int t = lane; t < tiles; t += 32) {
+      sl += __ldcg(&n.partial[((int64_t)m * n.tiles_cap + t) * 2 + 0]);
+      sq += __ldcg(&n.partial[((int64_t)m * n.tiles_cap + t) * 2 + 1]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sl += __shfl_down_sync(0xffffffffu, sl, o);
+      sq += __shfl_down_sync(0xffffffffu, sq, o);
     }
     loss += (0.5f * (sl / denom) + 0.5f * (sq / denom)) / (float)a.ensemble;
   }
+  if (lane != 0) return;
   const int it = st->iterations;
   const float t = (float)(it + 1);
   st->lr_t = schedule_lr(opt, it) * sqrtf(1.0f - powf(opt.beta2, t)) / (1.0f - powf(opt.beta1, t));
   st->loss = loss;
-  if (a.out_loss) *a.out_loss = loss;
+  if (n.out_loss) *n.out_loss = loss;
   if (desc != nullptr && desc->losses != nullptr) desc->losses[st->fit_step] = loss;
   st->nll_ticket = 0;
 }
@@ -276,51 +331,74 @@ __global__ void val_finalize_kernel(const double* acc, int ensemble, double deno
 // ---------------------------------------------------------------------------------------------
 // backward through one Dense + ReLU: dZ_{l-1} = (H_{l-1} > 0) * (dZ_l . W_l^T)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreadsF)
 train_backward_kernel(LayerArgs a, const FitDesc* desc, const TrainState* st, int rows_fixed) {
   const int rows = resolve_rows(desc, st, rows_fixed);
-  const int e = blockIdx.z, r0 = blockIdx.y * kTileM, k0 = blockIdx.x * kTileN;
+  const int e = blockIdx.z, r0 = blockIdx.y * kRowsF, k0 = blockIdx.x * kTileN;
   if (r0 >= rows) return;
-  __shared__ float Zs[kTileM][kTileK + 1];
-  __shared__ float Ws[kTileN][kTileK + 1];
+  __shared__ float Zs[kRowsF][kChunk + 1];
+  __shared__ float Ws[kTileN][kChunk + 1];
   const float* dZ = a.dz + e * a.dz_estride;
   const float* W = a.theta + e * a.pn + a.off;
   const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
-  float acc[2][4] = {};
-  for (int n0 = 0; n0 < a.N; n0 += kTileK) {
-    for (int i = tid; i < kTileM * kTileK; i += kThreads) {
-      const int r = i >> 5, n = i & 31;
-      Zs[r][n] = (r0 + r < rows && n0 + n < a.N) ? dZ[(int64_t)(r0 + r) * a.N + n0 + n] : 0.0f;
-    }
-    for (int i = tid; i < kTileN * kTileK; i += kThreads) {
-      const int k = i >> 5, n = i & 31;
-      Ws[k][n] = (k0 + k < a.K && n0 + n < a.N) ? W[(int64_t)(k0 + k) * a.N + n0 + n] : 0.0f;
-    }
-    __syncthreads();
+  float acc[4] = {};
+  for (int n0 = 0; n0 < a.N; n0 += kChunk) {
+    const int nc = min(kChunk, a.N - n0);
+    if (n0) __syncthreads();
+    float zv[kRowsF * kChunk / kThreadsF];
 #pragma unroll
-    for (int n = 0; n < kTileK; ++n) {
-      const float z0 = Zs[ty * 2][n], z1 = Zs[ty * 2 + 1][n];
+    for (int j = 0; j < kRowsF * kChunk / kThreadsF; ++j) {
+      const int i = tid + j * kThreadsF, r = i >> 7, n = i & (kChunk - 1);
+      zv[j] = (r0 + r < rows && n < nc) ? __ldcg(dZ + (int64_t)(r0 + r) * a.N + n0 + n) : 0.0f;
+    }
+    if ((a.N & 3) == 0) {
+      float4 wv[kTileN * kChunk / 4 / kThreadsF];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float w = Ws[tx * 4 + j][n];
-        acc[0][j] = fmaf(z0, w, acc[0][j]);
-        acc[1][j] = fmaf(z1, w, acc[1][j]);
+      for (int j = 0; j < kTileN * kChunk / 4 / kThreadsF; ++j) {
+        const int i = tid + j * kThreadsF, k = i >> 5, n = (i & 31) * 4;
+        wv[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (k0 + k < a.K && n < nc)
+          wv[j] = __ldcg(reinterpret_cast<const float4*>(W + (int64_t)(k0 + k) * a.N + n0 + n));
+      }
+#pragma unroll
+      for (int j = 0; j < kTileN * kChunk / 4 / kThreadsF; ++j) {
+        const int i = tid + j * kThreadsF, k = i >> 5, n = (i & 31) * 4;
+        Ws[k][n] = wv[j].x; Ws[k][n + 1] = wv[j].y; Ws[k][n + 2] = wv[j].z; Ws[k][n + 3] = wv[j].w;
+      }
+    } else {
+      float wv[kTileN * kChunk / kThreadsF];
+#pragma unroll
+      for (int j = 0; j < kTileN * kChunk / kThreadsF; ++j) {
+        const int i = tid + j * kThreadsF, k = i >> 7, n = i & (kChunk - 1);
+        wv[j] = (k0 + k < a.K && n < nc) ? __ldcg(W + (int64_t)(k0 + k) * a.N + n0 + n) : 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < kTileN * kChunk / kThreadsF; ++j) {
+        const int i = tid + j * kThreadsF;
+        Ws[i >> 7][i & (kChunk - 1)] = wv[j];
       }
     }
-    __syncthreads();
-  }
-  const float* H = a.in + e * a.in_estride;      // H_{l-1} after ReLU: > 0 <=> the unit was active
-  float* out = a.out + e * a.out_estride;
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int r = r0 + ty * 2 + i;
-    if (r >= rows) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = k0 + tx * 4 + j;
-      if (k >= a.K) continue;
-      out[(int64_t)r * a.K + k] = H[(int64_t)r * a.K + k] > 0.0f ? acc[i][j] : 0.0f;
+    for (int j = 0; j < kRowsF * kChunk / kThreadsF; ++j) {
+      const int i = tid + j * kThreadsF;
+      Zs[i >> 7][i & (kChunk - 1)] = zv[j];
     }
+    __syncthreads();
+#pragma unroll 8
+    for (int n = 0; n < nc; ++n) {
+      const float z = Zs[ty][n];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(z, Ws[tx * 4 + j][n], acc[j]);
+    }
+  }
+  const int r = r0 + ty;
+  if (r >= rows) return;
+  const float* H = a.in + e * a.in_estride + (int64_t)r * a.K;   // post-ReLU: > 0 <=> unit active
+  float* out = a.out + e * a.out_estride + (int64_t)r * a.K;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k = k0 + tx * 4 + j;
+    if (k < a.K) out[k] = H[k] > 0.0f ? acc[j] : 0.0f;
   }
 }
 
@@ -334,6 +412,7 @@ struct UpdLayer {
   const float* dz;      // [E][rows][N]
   int64_t dz_estride;
   int off, K, N;
+  int gather_h;         // layer 0 inside fit: rows follow the batch index
 };
 constexpr int kMaxTrainLayers = 18;
 struct UpdArgs {
@@ -344,60 +423,80 @@ struct UpdArgs {
   float* v;
   float* grad;
   int64_t pn;
+  int ensemble;
 };
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreadsU)
 train_update_kernel(UpdArgs a, OptParams opt, const FitDesc* desc, TrainState* st, int rows_fixed) {
   const int rows = resolve_rows(desc, st, rows_fixed);
   const UpdTile tile = a.tiles[blockIdx.x];
   const UpdLayer& L = a.layers[tile.layer];
   const int e = blockIdx.y;
-  __shared__ float Hs[kTileK][kTileK + 1];
-  __shared__ __align__(16) float Zs[kTileK][kTileN];
+  __shared__ float Hs[kRowsU][kTileN + 1];
+  __shared__ __align__(16) float Zs[kRowsU][kTileN];
   const float* H = L.h + e * L.h_estride;
   const float* dZ = L.dz + e * L.dz_estride;
+  const int* gidx = L.gather_h ? batch_rows_of(desc, st, e, a.ensemble) : nullptr;
   const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+  // the Adam operands are fetched while the gradient tile is being computed
+  const int k = tile.k0 + ty;
+  float th[4], mo[4], ve[4];
+  const int64_t p0 = e * a.pn + L.off + (int64_t)k * L.N + tile.n0 + tx * 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool ok = k <= L.K && tile.n0 + tx * 4 + j < L.N;
+    th[j] = ok ? a.theta[p0 + j] : 0.0f;
+    mo[j] = ok ? a.m[p0 + j] : 0.0f;
+    ve[j] = ok ? a.v[p0 + j] : 0.0f;
+  }
   float acc[4] = {};
-  for (int r0 = 0; r0 < rows; r0 += kTileK) {
-    for (int i = tid; i < kTileK * kTileK; i += kThreads) {
-      const int r = i >> 5, k = i & 31;
-      float h = 0.0f;
+  for (int r0 = 0; r0 < rows; r0 += kRowsU) {
+    if (r0) __syncthreads();
+    float hv[kRowsU * kTileN / kThreadsU], zv[kRowsU * kTileN / kThreadsU];
+#pragma unroll
+    for (int j = 0; j < kRowsU * kTileN / kThreadsU; ++j) {
+      const int i = tid + j * kThreadsU, r = i >> 5, kk = i & 31;
+      float h = 0.0f, z = 0.0f;
       if (r0 + r < rows) {
-        if (tile.k0 + k < L.K) h = H[(int64_t)(r0 + r) * L.K + tile.k0 + k];
-        else if (tile.k0 + k == L.K) h = 1.0f;          // the bias row
+        if (tile.k0 + kk < L.K) {
+          const float* row = gidx ? desc->inputs + (int64_t)gidx[r0 + r] * L.K : H + (int64_t)(r0 + r) * L.K;
+          h = __ldcg(row + tile.k0 + kk);
+        } else if (tile.k0 + kk == L.K) {
+          h = 1.0f;                                   // the bias row
+        }
+        if (tile.n0 + kk < L.N) z = __ldcg(dZ + (int64_t)(r0 + r) * L.N + tile.n0 + kk);
       }
-      Hs[r][k] = h;
+      hv[j] = h;
+      zv[j] = z;
     }
-    for (int i = tid; i < kTileK * kTileN; i += kThreads) {
-      const int r = i >> 5, n = i & 31;
-      Zs[r][n] = (r0 + r < rows && tile.n0 + n < L.N) ? dZ[(int64_t)(r0 + r) * L.N + tile.n0 + n] : 0.0f;
+#pragma unroll
+    for (int j = 0; j < kRowsU * kTileN / kThreadsU; ++j) {
+      const int i = tid + j * kThreadsU;
+      Hs[i >> 5][i & 31] = hv[j];
+      Zs[i >> 5][i & 31] = zv[j];
     }
     __syncthreads();
-#pragma unroll
-    for (int r = 0; r < kTileK; ++r) {
+#pragma unroll 8
+    for (int r = 0; r < kRowsU; ++r) {
       const float h = Hs[r][ty];
       const float4 z = *reinterpret_cast<const float4*>(&Zs[r][tx * 4]);
       acc[0] = fmaf(h, z.x, acc[0]); acc[1] = fmaf(h, z.y, acc[1]);
       acc[2] = fmaf(h, z.z, acc[2]); acc[3] = fmaf(h, z.w, acc[3]);
     }
-    __syncthreads();
   }
   const float lr_t = st->lr_t;
-  const int k = tile.k0 + ty;
   if (k <= L.K) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int n = tile.n0 + tx * 4 + j;
-      if (n >= L.N) continue;
-      const int64_t p = e * a.pn + L.off + (int64_t)k * L.N + n;
+      if (tile.n0 + tx * 4 + j >= L.N) continue;
       float g = acc[j];
-      a.grad[p] = g;
+      a.grad[p0 + j] = g;
       if (opt.clipvalue > 0.0f) g = fminf(fmaxf(g, -opt.clipvalue), opt.clipvalue);
-      const float m = a.m[p] + (1.0f - opt.beta1) * (g - a.m[p]);
-      const float v = a.v[p] + (1.0f - opt.beta2) * (g * g - a.v[p]);
-      a.m[p] = m;
-      a.v[p] = v;
-      a.theta[p] -= lr_t * m / (sqrtf(v) + opt.epsilon);
+      const float m = mo[j] + (1.0f - opt.beta1) * (g - mo[j]);
+      const float v = ve[j] + (1.0f - opt.beta2) * (g * g - ve[j]);
+      a.m[p0 + j] = m;
+      a.v[p0 + j] = v;
+      a.theta[p0 + j] = th[j] - lr_t * m / (sqrtf(v) + opt.epsilon);
     }
   }
   // the last CTA advances optimizer.iterations and fit's step counter
@@ -430,8 +529,6 @@ struct simba_trainer {
   float *theta = nullptr, *m = nullptr, *v = nullptr, *grad = nullptr;
   std::vector<float*> act;           // act[l]: input of train layer l (act[0] = gathered x)
   std::vector<float*> dz;            // dz[l]: gradient w.r.t. the pre-activation of train layer l
-  float* raw = nullptr;
-  float* ybuf = nullptr;
   float* partial = nullptr;
   int tiles_cap = 0;
   double* val_acc = nullptr;
@@ -478,12 +575,12 @@ static int pull_member(simba_trainer_t* t, int e, float* theta_e) {
   float* dst = theta_e + t->off[t->L];
   for (int k = 0; k < U; ++k)
     for (int o = 0; o < O; ++o) {
-      dst[(size_t)k * 2 * O + o] = kern[(size_t)k * O + o];
-      dst[(size_t)k * 2 * O + O + o] = kern2[(size_t)k * O + o];
+      dst[(size_t)k * 2 * O + 2 * o] = kern[(size_t)k * O + o];
+      dst[(size_t)k * 2 * O + 2 * o + 1] = kern2[(size_t)k * O + o];
     }
   for (int o = 0; o < O; ++o) {
-    dst[(size_t)U * 2 * O + o] = bias[o];
-    dst[(size_t)U * 2 * O + O + o] = bias2[o];
+    dst[(size_t)U * 2 * O + 2 * o] = bias[o];
+    dst[(size_t)U * 2 * O + 2 * o + 1] = bias2[o];
   }
   return SIMBA_OK;
 }
@@ -498,11 +595,11 @@ static void split_layer(const simba_trainer_t* t, const float* theta_e, int laye
     memcpy(bias, src + nk, t->N[layer] * sizeof(float));
     return;
   }
-  const int U = t->U, O = t->O, c0 = layer == t->L ? 0 : O;
+  const int U = t->U, O = t->O, c0 = layer == t->L ? 0 : 1;
   const float* src = theta_e + t->off[t->L];
   for (int k = 0; k < U; ++k)
-    for (int o = 0; o < O; ++o) kernel[(size_t)k * O + o] = src[(size_t)k * 2 * O + c0 + o];
-  for (int o = 0; o < O; ++o) bias[o] = src[(size_t)U * 2 * O + c0 + o];
+    for (int o = 0; o < O; ++o) kernel[(size_t)k * O + o] = src[(size_t)k * 2 * O + 2 * o + c0];
+  for (int o = 0; o < O; ++o) bias[o] = src[(size_t)U * 2 * O + 2 * o + c0];
 }
 
 extern "C" int simba_trainer_destroy(simba_trainer_t* t) {
@@ -512,7 +609,7 @@ extern "C" int simba_trainer_destroy(simba_trainer_t* t) {
   cudaFree(t->theta); cudaFree(t->m); cudaFree(t->v); cudaFree(t->grad);
   for (float* p : t->act) cudaFree(p);
   for (float* p : t->dz) cudaFree(p);
-  cudaFree(t->raw); cudaFree(t->ybuf); cudaFree(t->partial); cudaFree(t->val_acc);
+  cudaFree(t->partial); cudaFree(t->val_acc);
   cudaFree(t->state); cudaFree(t->desc); cudaFree(t->upd_tiles);
   delete t;
   return SIMBA_OK;
@@ -577,9 +674,7 @@ extern "C" int simba_trainer_create(simba_model_t* model, const simba_trainer_co
     TRY_OR_FREE(cudaMalloc(&t->act[l], (size_t)E * R * t->K[l] * sizeof(float)));
     TRY_OR_FREE(cudaMalloc(&t->dz[l], (size_t)E * cfg->batch_size * t->N[l] * sizeof(float)));
   }
-  TRY_OR_FREE(cudaMalloc(&t->raw, (size_t)E * R * 2 * t->O * sizeof(float)));
-  TRY_OR_FREE(cudaMalloc(&t->ybuf, (size_t)E * cfg->batch_size * t->O * sizeof(float)));
-  t->tiles_cap = (int)((R + kTileM - 1) / kTileM);
+  t->tiles_cap = (int)((R + kRowsF - 1) / kRowsF) * ((2 * t->O + kTileN - 1) / kTileN);
   TRY_OR_FREE(cudaMalloc(&t->partial, (size_t)E * t->tiles_cap * 2 * sizeof(float)));
   TRY_OR_FREE(cudaMalloc(&t->val_acc, (size_t)E * 2 * sizeof(double)));
   TRY_OR_FREE(cudaMalloc(&t->state, sizeof(TrainState)));
@@ -588,32 +683,46 @@ extern "C" int simba_trainer_create(simba_model_t* model, const simba_trainer_co
   TRY_OR_FREE(cudaMemset(t->desc, 0, sizeof(FitDesc)));
   std::vector<UpdTile> tiles;
   for (int l = 0; l <= t->L; ++l)
-    for (int k0 = 0; k0 <= t->K[l]; k0 += kTileK)
+    for (int k0 = 0; k0 <= t->K[l]; k0 += kTileN)
       for (int n0 = 0; n0 < t->N[l]; n0 += kTileN) tiles.push_back({l, k0, n0});
   t->n_upd_tiles = (int)tiles.size();
   TRY_OR_FREE(cudaMalloc(&t->upd_tiles, tiles.size() * sizeof(UpdTile)));
   TRY_OR_FREE(cudaMemcpy(t->upd_tiles, tiles.data(), tiles.size() * sizeof(UpdTile),
                          cudaMemcpyHostToDevice));
 #undef TRY_OR_FREE
-  t->launches_per_step = (t->L + 1) + 1 + t->L + 1;
+  t->launches_per_step = 2 * t->L + 2;
   *out = t;
   return SIMBA_OK;
 }
 
-// forward through all train layers; x may be shared by the members (estride 0)
-static int enqueue_forward(simba_trainer_t* t, const float* x, int64_t x_estride, int grid_rows,
-                           int rows_fixed, const FitDesc* desc, cudaStream_t s) {
+// one launch per hidden layer, then the head fused with the likelihood. x may be shared by the
+// members (estride 0, validation) or gathered through the fit descriptor (gather = 1).
+static int enqueue_forward(simba_trainer_t* t, const float* x, int64_t x_estride, const float* y,
+                           int64_t y_estride, int gather, int grid_rows, int rows_fixed,
+                           const FitDesc* desc, int train, float* out_loss, cudaStream_t s) {
   const int64_t R = t->cap_rows;
+  const int row_tiles = (grid_rows + kRowsF - 1) / kRowsF;
   for (int l = 0; l <= t->L; ++l) {
     LayerArgs a{};
     a.in = l == 0 ? x : t->act[l];
     a.in_estride = l == 0 ? x_estride : R * t->K[l];
+    a.gather_in = l == 0 ? gather : 0;
     a.theta = t->theta; a.pn = t->pn; a.off = t->off[l]; a.K = t->K[l]; a.N = t->N[l];
-    a.out = l < t->L ? t->act[l + 1] : t->raw;
-    a.out_estride = R * t->N[l];
-    a.relu = l < t->L ? 1 : 0;
-    dim3 grid((a.N + kTileN - 1) / kTileN, (grid_rows + kTileM - 1) / kTileM, t->E);
-    train_forward_kernel<<<grid, kThreads, 0, s>>>(a, desc, t->state, rows_fixed);
+    a.ensemble = t->E;
+    dim3 grid((a.N + kTileN - 1) / kTileN, row_tiles, t->E);
+    if (l < t->L) {
+      a.out = t->act[l + 1];
+      a.out_estride = R * t->N[l];
+      train_forward_kernel<<<grid, kThreadsF, 0, s>>>(a, desc, t->state, rows_fixed);
+    } else {
+      NllArgs n{};
+      n.y = y; n.y_estride = y_estride; n.gather_y = gather;
+      n.d_raw = train ? t->dz[t->L] : nullptr;
+      n.d_estride = (int64_t)t->cfg.batch_size * 2 * t->O;
+      n.partial = t->partial; n.tiles_cap = t->tiles_cap;
+      n.out_dim = t->O; n.train = train; n.out_loss = out_loss;
+      train_head_nll_kernel<<<grid, kThreadsF, 0, s>>>(a, n, opt_params(t), desc, t->state, rows_fixed);
+    }
   }
   SIMBA_CUDA_TRY(cudaGetLastError());
   return SIMBA_OK;
@@ -623,38 +732,35 @@ static int enqueue_step(simba_trainer_t* t, const float* x, int64_t x_estride, c
                         int64_t y_estride, int rows_fixed, const FitDesc* desc, float* out_loss,
                         cudaStream_t s) {
   const int64_t R = t->cap_rows, B = t->cfg.batch_size;
+  const int gather = desc ? 1 : 0;
   const int grid_rows = desc ? t->cfg.batch_size : rows_fixed;
-  const OptParams opt = opt_params(t);
-  int rc = enqueue_forward(t, x, x_estride, grid_rows, rows_fixed, desc, s);
+  int rc = enqueue_forward(t, x, x_estride, y, y_estride, gather, grid_rows, rows_fixed, desc, 1,
+                           out_loss, s);
   if (rc) return rc;
-  const int row_tiles = (grid_rows + kTileM - 1) / kTileM;
-  NllArgs n{};
-  n.raw = t->raw; n.raw_estride = R * 2 * t->O;
-  n.y = y; n.y_estride = y_estride;
-  n.d_raw = t->dz[t->L]; n.d_estride = B * 2 * t->O;
-  n.partial = t->partial; n.tiles_cap = t->tiles_cap;
-  n.out_dim = t->O; n.ensemble = t->E; n.train = 1; n.out_loss = out_loss;
-  train_nll_kernel<<<dim3(row_tiles, t->E), kThreads, 0, s>>>(n, opt, desc, t->state, rows_fixed);
+  const int row_tiles = (grid_rows + kRowsF - 1) / kRowsF;
   for (int l = t->L; l >= 1; --l) {
     LayerArgs a{};
     a.in = t->act[l]; a.in_estride = R * t->K[l];       // H_{l-1}: the (ReLU) input of layer l
     a.theta = t->theta; a.pn = t->pn; a.off = t->off[l]; a.K = t->K[l]; a.N = t->N[l];
     a.dz = t->dz[l]; a.dz_estride = B * t->N[l];
     a.out = t->dz[l - 1]; a.out_estride = B * t->N[l - 1];   // N_{l-1} == K_l
+    a.ensemble = t->E;
     dim3 grid((a.K + kTileN - 1) / kTileN, row_tiles, t->E);
-    train_backward_kernel<<<grid, kThreads, 0, s>>>(a, desc, t->state, rows_fixed);
+    train_backward_kernel<<<grid, kThreadsF, 0, s>>>(a, desc, t->state, rows_fixed);
   }
   UpdArgs u{};
   for (int l = 0; l <= t->L; ++l) {
     u.layers[l].h = l == 0 ? x : t->act[l];
     u.layers[l].h_estride = l == 0 ? x_estride : R * t->K[l];
+    u.layers[l].gather_h = l == 0 ? gather : 0;
     u.layers[l].dz = t->dz[l];
     u.layers[l].dz_estride = B * t->N[l];
     u.layers[l].off = t->off[l]; u.layers[l].K = t->K[l]; u.layers[l].N = t->N[l];
   }
   u.tiles = t->upd_tiles; u.theta = t->theta; u.m = t->m; u.v = t->v; u.grad = t->grad; u.pn = t->pn;
-  train_update_kernel<<<dim3(t->n_upd_tiles, t->E), kThreads, 0, s>>>(u, opt, desc, t->state,
-                                                                      rows_fixed);
+  u.ensemble = t->E;
+  train_update_kernel<<<dim3(t->n_upd_tiles, t->E), kThreadsU, 0, s>>>(u, opt_params(t), desc,
+                                                                        t->state, rows_fixed);
   SIMBA_CUDA_TRY(cudaGetLastError());
   return SIMBA_OK;
 }
@@ -685,12 +791,7 @@ extern "C" int simba_trainer_fit(simba_trainer_t* t, const float* inputs, const 
     if (!t->graph_stream) SIMBA_CUDA_TRY(cudaStreamCreateWithFlags(&t->graph_stream, cudaStreamNonBlocking));
     cudaGraph_t graph = nullptr;
     SIMBA_CUDA_TRY(cudaStreamBeginCapture(t->graph_stream, cudaStreamCaptureModeThreadLocal));
-    const int width = t->IN + t->O;
-    gather_batch_kernel<<<dim3((B * width + 255) / 256, t->E), 256, 0, t->graph_stream>>>(
-        t->desc, t->state, B, t->IN, t->O, t->act[0], t->ybuf, (int64_t)t->cap_rows * t->IN,
-        (int64_t)B * t->O);
-    int rc = enqueue_step(t, t->act[0], (int64_t)t->cap_rows * t->IN, t->ybuf, (int64_t)B * t->O, B,
-                          t->desc, nullptr, t->graph_stream);
+    int rc = enqueue_step(t, nullptr, 0, nullptr, 0, B, t->desc, nullptr, t->graph_stream);
     cudaError_t ce = cudaStreamEndCapture(t->graph_stream, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     SIMBA_CUDA_TRY(ce);
@@ -707,19 +808,11 @@ extern "C" int simba_trainer_validation(simba_trainer_t* t, const float* x, cons
   if (!t || !x || !y || !out_loss) return set_error(SIMBA_ERR_BAD_CONFIG, "null argument");
   if (rows < 1) return set_error(SIMBA_ERR_SHAPE, "rows %lld", (long long)rows);
   cudaStream_t s = (cudaStream_t)stream;
-  const OptParams opt = opt_params(t);
   for (int64_t r0 = 0; r0 < rows; r0 += t->cap_rows) {
     const int nr = (int)((rows - r0) < t->cap_rows ? (rows - r0) : t->cap_rows);
-    int rc = enqueue_forward(t, x + r0 * t->IN, 0, nr, nr, nullptr, s);
+    int rc = enqueue_forward(t, x + r0 * t->IN, 0, y + r0 * t->O, 0, 0, nr, nr, nullptr, 0, nullptr, s);
     if (rc) return rc;
-    const int tiles = (nr + kTileM - 1) / kTileM;
-    NllArgs n{};
-    n.raw = t->raw; n.raw_estride = (int64_t)t->cap_rows * 2 * t->O;
-    n.y = y + r0 * t->O; n.y_estride = 0;
-    n.d_raw = nullptr;
-    n.partial = t->partial; n.tiles_cap = t->tiles_cap;
-    n.out_dim = t->O; n.ensemble = t->E; n.train = 0; n.out_loss = nullptr;
-    train_nll_kernel<<<dim3(tiles, t->E), kThreads, 0, s>>>(n, opt, nullptr, t->state, nr);
+    const int tiles = ((nr + kRowsF - 1) / kRowsF) * ((2 * t->O + kTileN - 1) / kTileN);
     val_accumulate_kernel<<<1, 32, 0, s>>>(t->partial, t->tiles_cap, tiles, t->E, t->val_acc,
                                            r0 == 0 ? 1 : 0);
   }
