@@ -3,21 +3,28 @@
 // (simba/models/mlp_ensemble.py:134-187). fp32 throughout — the reference trains in fp32 and the
 // planner's fp32 and bf16 weight images are both derived from these master weights.
 //
-// Shape of the work: E members x batch 64 x a 4x128 MLP is 28 MFLOP per member-step, far below
-// what one launch can hide, so the step is latency-bound. The design goal is therefore few, wide
-// launches that stay inside one CUDA graph:
-//   forward   L launches     H_l = relu([H_{l-1}, 1] . theta_l)    grid (N/32, rows/16, E)
-//   head+nll  1 launch       mu, var, loss, d(mu), d(raw var), lr_t (mu / var stay in registers)
-//   backward  L launches     dZ_{l-1} = relu'(H) * (dZ_l . W_l^T)  grid (K/32, rows/16, E)
-//   update    1 launch       dtheta = [H, 1]^T . dZ for EVERY layer, clip, Adam, in one grid
-// i.e. 2L + 2 launches per step; fit()'s batch gather is folded into the kernels that read the
-// batch. Every CTA stages its whole (<= 128-deep) contraction with one wave of loads, so it pays
-// the memory latency once, and the tiles are small so that one layer spreads over ~80 SMs.
-// Parameters of train layer l are stored as one [(K_l + 1) x N_l] row-major block (Keras kernel
-// [in, out] followed by the bias row), so "bias" is just the row that multiplies the constant 1
-// and the weight-gradient GEMM produces the bias gradient as its last row. The Gaussian head's
-// two Dense layers (mlp_ensemble.py:28-30) are one block with N = 2 * O whose columns interleave
-// (mu_0, var_0, mu_1, var_1, ...). Reductions are in a fixed order: results are bit-reproducible.
+// Shape of the work: E members x batch 64 x a 4x128 MLP is 28 MFLOP per member-step — nothing a
+// launch can hide — so the step is latency-bound and the design minimises dependent launches and
+// dependent memory round trips. Forward and back-propagation of the activations are ROW-LOCAL
+// (row r of every H_l and dZ_l depends only on row r of the batch), so one CTA walks a 16-row
+// tile through the whole chain without any inter-CTA dependency:
+//   chain   1 launch   H_{l+1} = relu([H_l, 1] . theta_l), l < L; head -> (mu, var) -> likelihood,
+//                      d(mu), d(raw var), lr_t; then dZ_{l-1} = relu'(H_l) * (dZ_l . theta_l^T),
+//                      l = L..1. Weights stream from L2 as TMA bulk copies (cp.async.bulk +
+//                      mbarrier) into a two-chunk ring — chunk q + 1 lands while chunk q is
+//                      multiplied; activations stay in shared memory between layers and are
+//                      written out once for the update kernel.
+//   update  1 launch   dtheta_l = [H_l, 1]^T . dZ_l for EVERY layer, clip, Adam — one grid
+// i.e. 2 launches per step (one CUDA graph), and fit()'s batch gather is folded into the loads.
+// Parameters of train layer l are one [(K_l + 1) x N_l] row-major block (Keras kernel [in, out]
+// followed by the bias row): "bias" is the row that multiplies the constant 1, and the
+// weight-gradient GEMM yields the bias gradient as its last row. The Gaussian head's two Dense
+// layers (mlp_ensemble.py:28-30) are one block with N = 2 * O whose columns interleave
+// (mu_0, var_0, mu_1, var_1, ...), so a thread's accumulators hold complete (mu, var) pairs and
+// mu / var never go to memory. The update kernel also maintains theta_l^T, so back-propagation
+// reads its weights with the same unit-stride tile pattern as the forward pass.
+// Reductions are in a fixed order: results are bit-reproducible run to run.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -29,13 +36,14 @@ using namespace simba;
 
 namespace {
 
-constexpr int kRowsF = 16;     // rows per CTA in forward / backward (more, smaller CTAs: the step is
-                               // latency-bound, so the work is spread over as many SMs as possible)
-constexpr int kTileN = 32;     // output columns per CTA
-constexpr int kChunk = 128;    // contraction chunk staged in shared memory in ONE load phase
-constexpr int kThreadsF = 128;
-constexpr int kRowsU = 64;     // batch rows per chunk in the weight-gradient kernel
+constexpr int kRows = 16;        // batch rows per chain CTA
+constexpr int kChunkK = 64;      // weight chunk: [64 k] x [128 n] fp32 = 32 KB, two in flight
+constexpr int kChunkN = 128;
+constexpr int kChainThreads = 256;
+constexpr int kTileU = 32;       // update kernel: [32 k] x [32 n] tile of dtheta
+constexpr int kRowsU = 64;       // update kernel: batch rows per staged chunk
 constexpr int kThreadsU = 256;
+constexpr int kMaxTrainLayers = 18;
 
 struct TrainState {
   int iterations;        // optimizer.iterations
@@ -77,129 +85,47 @@ __global__ void set_fit_desc_kernel(FitDesc d, FitDesc* out, TrainState* st) {
   st->fit_step = 0;
 }
 
-// ---------------------------------------------------------------------------------------------
-// forward: Y = act(X . W + b) — BaseLayer.call / GaussianHead.call (mlp_ensemble.py:17-22, :32-34)
-// ---------------------------------------------------------------------------------------------
-struct LayerArgs {
-  const float* in;        // [E][rows][K]   (e-stride may be 0: validation shares its rows)
-  int64_t in_estride;
-  int gather_in;          // 1: rows of `in` are desc->inputs[batch_index[...]] (layer 0 inside fit)
-  const float* theta;     // [E][pn]
-  int64_t pn;
-  int off, K, N;
-  float* out;             // forward: [E][rows][N]; backward: dZ_{l-1} [E][rows][K]
-  int64_t out_estride;
-  const float* dz;        // backward only: dZ_l [E][rows][N]
-  int64_t dz_estride;
-  int ensemble;
-};
-
-// acc[j] = sum_k X[r0 + ty][k] * W[k][n0 + tx * 4 + j]; all of a <= 128-deep contraction is staged
-// by one wave of loads, so a CTA pays the memory latency once
-__device__ __forceinline__ void forward_tile(const LayerArgs& a, const FitDesc* desc,
-                                             const TrainState* st, int rows, int e, int r0, int n0,
-                                             float (&Xs)[kRowsF][kChunk + 1],
-                                             float (&Ws)[kChunk][kTileN], float (&acc)[4]) {
-  const float* W = a.theta + e * a.pn + a.off;
-  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
-  const float* X = a.in + e * a.in_estride;
-  const int* gidx = a.gather_in ? batch_rows_of(desc, st, e, a.ensemble) : nullptr;
-  const bool vec = (a.N & 3) == 0;      // then every block offset and row of W is 16-byte aligned
-  for (int k0 = 0; k0 < a.K; k0 += kChunk) {
-    const int kc = min(kChunk, a.K - k0);
-    if (k0) __syncthreads();
-    // all global loads of the chunk are issued into registers before the first shared store, so
-    // the CTA waits for memory once (the step is latency-bound, not bandwidth-bound)
-    float xv[kRowsF * kChunk / kThreadsF];
-#pragma unroll
-    for (int j = 0; j < kRowsF * kChunk / kThreadsF; ++j) {
-      const int i = tid + j * kThreadsF, r = i >> 7, k = i & (kChunk - 1);
-      xv[j] = 0.0f;
-      if (r0 + r < rows && k < kc) {
-        const float* row = gidx ? desc->inputs + (int64_t)gidx[r0 + r] * a.K : X + (int64_t)(r0 + r) * a.K;
-        xv[j] = __ldg(row + k0 + k);
-      }
-    }
-    if (vec) {
-      float4 wv[kChunk * kTileN / 4 / kThreadsF];
-#pragma unroll
-      for (int j = 0; j < kChunk * kTileN / 4 / kThreadsF; ++j) {
-        const int i = tid + j * kThreadsF, k = i >> 3, n = (i & 7) * 4;
-        wv[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (k < kc && n0 + n < a.N)
-          wv[j] = __ldcg(reinterpret_cast<const float4*>(W + (int64_t)(k0 + k) * a.N + n0 + n));
-      }
-#pragma unroll
-      for (int j = 0; j < kChunk * kTileN / 4 / kThreadsF; ++j) {
-        const int i = tid + j * kThreadsF;
-        *reinterpret_cast<float4*>(&Ws[i >> 3][(i & 7) * 4]) = wv[j];
-      }
-    } else {
-      float wv[kChunk * kTileN / kThreadsF];
-#pragma unroll
-      for (int j = 0; j < kChunk * kTileN / kThreadsF; ++j) {
-        const int i = tid + j * kThreadsF, k = i >> 5, n = i & 31;
-        wv[j] = (k < kc && n0 + n < a.N) ? __ldcg(W + (int64_t)(k0 + k) * a.N + n0 + n) : 0.0f;
-      }
-#pragma unroll
-      for (int j = 0; j < kChunk * kTileN / kThreadsF; ++j) {
-        const int i = tid + j * kThreadsF;
-        Ws[i >> 5][i & 31] = wv[j];
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < kRowsF * kChunk / kThreadsF; ++j) {
-      const int i = tid + j * kThreadsF;
-      Xs[i >> 7][i & (kChunk - 1)] = xv[j];
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int k = 0; k < kc; ++k) {
-      const float x = Xs[ty][k];
-      const float4 w = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
-      acc[0] = fmaf(x, w.x, acc[0]); acc[1] = fmaf(x, w.y, acc[1]);
-      acc[2] = fmaf(x, w.z, acc[2]); acc[3] = fmaf(x, w.w, acc[3]);
-    }
+// ---- PTX wrappers: mbarrier + TMA bulk copy (cp.async.bulk) -----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded: a protocol bug must fault the kernel, never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
   }
 }
-
-__global__ void __launch_bounds__(kThreadsF)
-train_forward_kernel(LayerArgs a, const FitDesc* desc, const TrainState* st, int rows_fixed) {
-  const int rows = resolve_rows(desc, st, rows_fixed);
-  const int e = blockIdx.z, r0 = blockIdx.y * kRowsF, n0 = blockIdx.x * kTileN;
-  if (r0 >= rows) return;
-  __shared__ float Xs[kRowsF][kChunk + 1];
-  __shared__ __align__(16) float Ws[kChunk][kTileN];
-  float acc[4] = {};
-  forward_tile(a, desc, st, rows, e, r0, n0, Xs, Ws, acc);
-  const int tx = threadIdx.x & 7, r = r0 + (threadIdx.x >> 3);
-  if (r >= rows) return;
-  const float* bias = a.theta + e * a.pn + a.off + (int64_t)a.K * a.N;
-  float* Y = a.out + e * a.out_estride + (int64_t)r * a.N;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int n = n0 + tx * 4 + j;
-    if (n < a.N) Y[n] = fmaxf(acc[j] + bias[n], 0.0f);
-  }
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-
-// ---------------------------------------------------------------------------------------------
-// Gaussian head + negative_log_likelihood (mlp_ensemble.py:28-34, :64-67) + its gradient w.r.t.
-// the head pre-activations, fused: the head block stores (mu_o, var_o) in adjacent columns, so a
-// thread's four accumulators are two complete outputs and mu / var never go to memory.
-// ---------------------------------------------------------------------------------------------
-struct NllArgs {
-  const float* y;          // [E][rows][O] (ignored when gather_y)
-  int64_t y_estride;
-  int gather_y;            // 1: rows of y are desc->targets[batch_index[...]]
-  float* d_raw;            // [E][rows][2 O] (interleaved like the head block) or null (validation)
-  int64_t d_estride;
-  float* partial;          // [E][tiles_cap][2]
-  int tiles_cap;
-  int out_dim;
-  int train;               // 1: last CTA finalises the loss and the step's lr_t
-  float* out_loss;         // device [1] or null
-};
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
 
 __device__ __forceinline__ float block_sum(float v, float* scratch) {
   // fixed-order tree: shuffles inside the warp, then thread 0 adds the warp sums in order
@@ -221,74 +147,315 @@ __device__ float schedule_lr(const OptParams& o, int iterations) {
   return fmaxf(o.lr0 * (1.0f - epochs / (float)o.train_epochs), 0.0f);
 }
 
-__global__ void __launch_bounds__(kThreadsF)
-train_head_nll_kernel(LayerArgs a, NllArgs n, OptParams opt, const FitDesc* desc, TrainState* st,
-                      int rows_fixed) {
-  const int rows = resolve_rows(desc, st, rows_fixed);
-  const int e = blockIdx.z, r0 = blockIdx.y * kRowsF, n0 = blockIdx.x * kTileN;
-  const int O = n.out_dim;
-  __shared__ float Xs[kRowsF][kChunk + 1];
-  __shared__ __align__(16) float Ws[kChunk][kTileN];
-  __shared__ float scratch[kThreadsF / 32];
-  __shared__ bool last;
-  float s_log = 0.0f, s_sq = 0.0f;
-  if (r0 < rows) {
-    float acc[4] = {};
-    forward_tile(a, desc, st, rows, e, r0, n0, Xs, Ws, acc);
-    const int tx = threadIdx.x & 7, r = r0 + (threadIdx.x >> 3);
-    if (r < rows) {
-      const float c = 1.0f / ((float)rows * (float)O * (float)a.ensemble);
-      const float* bias = a.theta + e * a.pn + a.off + (int64_t)a.K * a.N;
-      const float* y = n.gather_y
-          ? desc->targets + (int64_t)batch_rows_of(desc, st, e, a.ensemble)[r] * O
-          : n.y + e * n.y_estride + (int64_t)r * O;
-      float* d = n.d_raw ? n.d_raw + e * n.d_estride + (int64_t)r * 2 * O : nullptr;
-#pragma unroll
-      for (int j = 0; j < 4; j += 2) {
-        const int col = n0 + tx * 4 + j;
-        if (col >= a.N) continue;
-        const int o = col >> 1;
-        const float mu = acc[j] + bias[col];
-        const float pre = acc[j + 1] + bias[col + 1];
-        const float var = softplus_tf(pre) + 1e-4f;
-        const float diff = mu - y[o];
-        const float inv = 1.0f / var;
-        s_log += logf(6.28318530717958647692f * var);
-        s_sq += diff * diff * inv;
-        if (d) {
-          d[col] = c * diff * inv;
-          const float sig = 1.0f / (1.0f + expf(-pre));
-          d[col + 1] = 0.5f * c * (inv - diff * diff * inv * inv) * sig;
-        }
+// ---------------------------------------------------------------------------------------------
+// chain kernel: forward (BaseLayer.call / GaussianHead.call, mlp_ensemble.py:17-22, :28-34),
+// negative_log_likelihood (:64-67) with its gradient, and the activation back-propagation
+// ---------------------------------------------------------------------------------------------
+#ifdef SIMBA_TRAIN_TIMELINE
+__device__ long long g_train_tl[512];
+#define TL(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_train_tl[(slot)] = clock64(); } while (0)
+#else
+#define TL(slot) do { } while (0)
+#endif
+
+enum PassKind { kPassHidden = 0, kPassHead = 1, kPassBackward = 2 };
+
+// one GEMM of the chain: out[16 x n_dim] = in[16 x k_dim] . W[k_dim x n_dim]   (W row-major, ld = n_dim)
+struct ChainPass {
+  int64_t w_off;          // into theta (forward / head) or theta^T (backward), per member
+  int64_t bias_off;       // forward / head: the bias row inside theta
+  int k_dim, n_dim;
+  int kind;
+  float* out;             // hidden: H_{l+1} [E][cap][n]; head: dZ_L [E][B][n]; backward: dZ_{l-1}
+  int64_t out_estride;
+  const float* mask;      // backward: H_l [E][cap][n_dim of this pass]; > 0 <=> the unit was active
+  int64_t mask_estride;
+};
+
+struct ChainArgs {
+  ChainPass pass[2 * kMaxTrainLayers];
+  int n_forward;          // hidden layers + head
+  int n_pass;             // n_forward (+ backward passes when training)
+  const float* x;         // [E][rows][K_0] (estride may be 0: validation shares its rows)
+  int64_t x_estride;
+  int gather;             // 1: batch rows follow the fit descriptor's index
+  const float* y;         // [E][rows][O]
+  int64_t y_estride;
+  const float* theta;     // [E][pn]
+  const float* thetaT;    // [E][pnT]
+  int64_t pn, pnT;
+  int ld_act;             // row stride of the shared activation tiles (widest layer)
+  int out_dim, ensemble;
+  int aligned;            // every chunk row is 16-byte aligned -> 16-byte cp.async
+  float* partial;         // [E][tiles_cap][2]
+  int tiles_cap;
+  int train;
+  float* out_loss;
+};
+
+struct ChunkCursor {      // walks the chunks of the chain in execution order
+  int pass, n0, k0;
+};
+
+__device__ __forceinline__ bool next_chunk(const ChainArgs& a, ChunkCursor& c) {
+  const ChainPass& p = a.pass[c.pass];
+  c.k0 += kChunkK;
+  if (c.k0 < p.k_dim) return true;
+  c.k0 = 0;
+  c.n0 += kChunkN;
+  if (c.n0 < p.n_dim) return true;
+  c.n0 = 0;
+  c.pass += 1;
+  return c.pass < a.n_pass;
+}
+
+// row stride of a weight chunk in shared memory: a layer no wider than one chunk is one contiguous
+// block of theta, copied by a single bulk instruction and kept at its own row stride
+__device__ __forceinline__ int chunk_stride(const ChainArgs& a, const ChainPass& p) {
+  return (a.aligned && p.n_dim <= kChunkN) ? p.n_dim : kChunkN;
+}
+
+// Requests chunk `c` into `buf`. Aligned shapes: TMA bulk copies issued by warp 0 (ONE instruction
+// when the layer is no wider than a chunk), completion on `bar`. Other shapes (tests with odd
+// widths): plain loads by every thread, visible after the caller's next __syncthreads. Rows
+// [kc, roundup4(kc)) are zeroed: the multiply consumes k in groups of 4.
+__device__ __forceinline__ void issue_chunk(const ChainArgs& a, const ChunkCursor& c, int e, float* buf,
+                                            uint32_t bar) {
+  const ChainPass& p = a.pass[c.pass];
+  const float* base = (p.kind == kPassBackward ? a.thetaT + e * a.pnT : a.theta + e * a.pn) + p.w_off;
+  const float* src = base + (int64_t)c.k0 * p.n_dim + c.n0;
+  const int kc = min(kChunkK, p.k_dim - c.k0), nc = min(kChunkN, p.n_dim - c.n0);
+  const int S = chunk_stride(a, p);
+  const int kc4 = (kc + 3) & ~3;
+  const int tid = threadIdx.x;
+  for (int i = kc * S + tid; i < kc4 * S; i += kChainThreads) buf[i] = 0.0f;
+  if (a.aligned) {
+    if (kc4 != kc) fence_proxy_async();
+    if (tid < 32) {
+      if (tid == 0) mbar_expect_tx(bar, (uint32_t)(kc * nc * sizeof(float)));
+      __syncwarp();
+      if (p.n_dim <= kChunkN) {
+        if (tid == 0) bulk_g2s(smem_u32(buf), src, (uint32_t)(kc * nc * sizeof(float)), bar);
+      } else {
+        for (int k = tid; k < kc; k += 32)
+          bulk_g2s(smem_u32(buf + k * S), src + (int64_t)k * p.n_dim, (uint32_t)(nc * sizeof(float)), bar);
       }
     }
+  } else {
+    for (int i = tid; i < kc * nc; i += kChainThreads) {
+      const int k = i / nc, n = i - k * nc;
+      buf[k * S + n] = __ldcg(src + (int64_t)k * p.n_dim + n);
+    }
   }
+}
+
+// The multiply is split-K across the 8 warps: warp w owns k-groups w, w + 8, ... of the chunk and
+// accumulates a full [16 x 128] partial tile in registers (lane -> 4 columns, 16 rows: 64
+// accumulators), so every weight element is read from shared memory exactly once per CTA and the
+// 64 independent FMA chains hide the shared-memory latency. The 8 partial tiles are added in warp
+// order through shared memory when the layer's last chunk is done.
+__global__ void __launch_bounds__(kChainThreads)
+train_chain_kernel(ChainArgs a, OptParams opt, const FitDesc* desc, TrainState* st, int rows_fixed) {
+  extern __shared__ __align__(16) float smem[];
+  float* red = smem + 2 * kChunkK * kChunkN;                 // [8 warps][16][128]
+  float* act0 = red + (kChainThreads / 32) * kRows * kChunkN;
+  float* act1 = act0 + kRows * a.ld_act;
+  __shared__ float scratch[kChainThreads / 32];
+  __shared__ __align__(8) unsigned long long bars[2];
+  __shared__ bool last;
+
+  const int rows = resolve_rows(desc, st, rows_fixed);
+  const int e = blockIdx.y, r0 = blockIdx.x * kRows;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rl = tid >> 4, cl = 8 * (tid & 15);     // epilogue: row rl, chunk-local columns cl .. cl + 7
+  const int ld = a.ld_act;
+  float s_log = 0.0f, s_sq = 0.0f;
+  TL(0);
+
+  if (r0 < rows) {
+    if (tid == 0) {
+      mbar_init(smem_u32(&bars[0]), 1);
+      mbar_init(smem_u32(&bars[1]), 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+    ChunkCursor cur{0, 0, 0}, nxt{0, 0, 0};
+    issue_chunk(a, cur, e, smem, smem_u32(&bars[0]));
+    bool more = next_chunk(a, nxt);
+    // the batch tile (layer 0 input), zero-padded to a multiple of 4 columns
+    {
+      const int K0 = a.pass[0].k_dim, K0r = (K0 + 3) & ~3;
+      const int* gidx = a.gather ? batch_rows_of(desc, st, e, a.ensemble) : nullptr;
+      const float* X = a.x + e * a.x_estride;
+      for (int i = tid; i < kRows * K0r; i += kChainThreads) {
+        const int r = i / K0r, k = i - r * K0r;
+        float v = 0.0f;
+        if (r0 + r < rows && k < K0) {
+          const float* row = gidx ? desc->inputs + (int64_t)gidx[r0 + r] * K0 : X + (int64_t)(r0 + r) * K0;
+          v = __ldg(row + k);
+        }
+        act0[r * ld + k] = v;
+      }
+    }
+    __syncthreads();
+    float* in = act0;
+    float* out = act1;
+    float acc[kRows][4] = {};
+    int q = 0;
+    TL(1);
+    while (true) {
+      const ChainPass& p = a.pass[cur.pass];
+      const float* wb = smem + (q & 1) * kChunkK * kChunkN;
+      TL(8 + q * 8 + 0);
+      if (more)
+        issue_chunk(a, nxt, e, smem + ((q + 1) & 1) * kChunkK * kChunkN, smem_u32(&bars[(q + 1) & 1]));
+      TL(8 + q * 8 + 1);
+      const int kc = min(kChunkK, p.k_dim - cur.k0);
+      const int kc4 = (kc + 3) & ~3;
+      const bool last_k = cur.k0 + kChunkK >= p.k_dim;
+      const int c0 = cur.n0 + cl;
+      const int r = r0 + rl;
+      const bool row_ok = r < rows;
+      // epilogue operands are requested before the multiply so their latency hides behind it
+      float pb[8] = {};                              // bias (forward / head)
+      float pm[8] = {};                              // backward: H_l (mask); head: targets at even j
+      if (last_k) {
+        if (p.kind != kPassBackward) {
+          const float* bias = a.theta + e * a.pn + p.bias_off;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (c0 + j < p.n_dim) pb[j] = __ldcg(bias + c0 + j);
+        }
+        if (row_ok) {
+          if (p.kind == kPassBackward) {
+            const float* h = p.mask + e * p.mask_estride + (int64_t)r * p.n_dim;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (c0 + j < p.n_dim) pm[j] = __ldcg(h + c0 + j);
+          } else if (p.kind == kPassHead) {
+            const float* y = a.gather
+                ? desc->targets + (int64_t)batch_rows_of(desc, st, e, a.ensemble)[r] * a.out_dim
+                : a.y + e * a.y_estride + (int64_t)r * a.out_dim;
+#pragma unroll
+            for (int j = 0; j < 8; j += 2)
+              if (c0 + j < p.n_dim) pm[j] = __ldg(y + ((c0 + j) >> 1));
+          }
+        }
+      }
+      if (a.aligned) mbar_wait(smem_u32(&bars[q & 1]), (q >> 1) & 1);
+      TL(8 + q * 8 + 2);
+      {
+        const int S = chunk_stride(a, p);
+        const float* w = wb + 4 * lane;
+        const float* xin = in + cur.k0;
+        for (int kk = 4 * warp; kk < kc4; kk += 4 * (kChainThreads / 32)) {
+          const float4 w0 = *reinterpret_cast<const float4*>(w + (kk + 0) * S);
+          const float4 w1 = *reinterpret_cast<const float4*>(w + (kk + 1) * S);
+          const float4 w2 = *reinterpret_cast<const float4*>(w + (kk + 2) * S);
+          const float4 w3 = *reinterpret_cast<const float4*>(w + (kk + 3) * S);
+#pragma unroll
+          for (int i = 0; i < kRows; ++i) {
+            const float4 x = *reinterpret_cast<const float4*>(xin + i * ld + kk);
+            acc[i][0] = fmaf(x.x, w0.x, acc[i][0]); acc[i][1] = fmaf(x.x, w0.y, acc[i][1]);
+            acc[i][2] = fmaf(x.x, w0.z, acc[i][2]); acc[i][3] = fmaf(x.x, w0.w, acc[i][3]);
+            acc[i][0] = fmaf(x.y, w1.x, acc[i][0]); acc[i][1] = fmaf(x.y, w1.y, acc[i][1]);
+            acc[i][2] = fmaf(x.y, w1.z, acc[i][2]); acc[i][3] = fmaf(x.y, w1.w, acc[i][3]);
+            acc[i][0] = fmaf(x.z, w2.x, acc[i][0]); acc[i][1] = fmaf(x.z, w2.y, acc[i][1]);
+            acc[i][2] = fmaf(x.z, w2.z, acc[i][2]); acc[i][3] = fmaf(x.z, w2.w, acc[i][3]);
+            acc[i][0] = fmaf(x.w, w3.x, acc[i][0]); acc[i][1] = fmaf(x.w, w3.y, acc[i][1]);
+            acc[i][2] = fmaf(x.w, w3.z, acc[i][2]); acc[i][3] = fmaf(x.w, w3.w, acc[i][3]);
+          }
+        }
+      }
+      TL(8 + q * 8 + 3);
+      if (last_k) {
+        // add the 8 warps' partial tiles in warp order, then the epilogue of row rl, columns c0..c0+7
+#pragma unroll
+        for (int i = 0; i < kRows; ++i) {
+          *reinterpret_cast<float4*>(red + (warp * kRows + i) * kChunkN + 4 * lane) =
+              make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+          acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
+        }
+        __syncthreads();
+        float v[8] = {};
+#pragma unroll
+        for (int w8 = 0; w8 < kChainThreads / 32; ++w8) {
+          const float4 lo = *reinterpret_cast<const float4*>(red + (w8 * kRows + rl) * kChunkN + cl);
+          const float4 hi = *reinterpret_cast<const float4*>(red + (w8 * kRows + rl) * kChunkN + cl + 4);
+          v[0] += lo.x; v[1] += lo.y; v[2] += lo.z; v[3] += lo.w;
+          v[4] += hi.x; v[5] += hi.y; v[6] += hi.z; v[7] += hi.w;
+        }
+        float* gout = p.out + e * p.out_estride + (int64_t)r * p.n_dim;
+        const bool store = row_ok && (p.kind != kPassHead || a.train);
+        if (p.kind == kPassHead) {
+          const float c = 1.0f / ((float)rows * (float)a.out_dim * (float)a.ensemble);
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            float d_mu = 0.0f, d_pre = 0.0f;
+            if (c0 + j < p.n_dim && row_ok) {
+              const float mu = v[j] + pb[j];
+              const float pre = v[j + 1] + pb[j + 1];
+              const float var = softplus_tf(pre) + 1e-4f;
+              const float diff = mu - pm[j];
+              const float inv = 1.0f / var;
+              s_log += logf(6.28318530717958647692f * var);
+              s_sq += diff * diff * inv;
+              d_mu = c * diff * inv;
+              d_pre = 0.5f * c * (inv - diff * diff * inv * inv) * (1.0f / (1.0f + expf(-pre)));
+            }
+            v[j] = d_mu;
+            v[j + 1] = d_pre;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const bool ok = c0 + j < p.n_dim;
+            if (p.kind == kPassHidden) v[j] = ok ? fmaxf(v[j] + pb[j], 0.0f) : 0.0f;
+            else v[j] = (ok && row_ok && pm[j] > 0.0f) ? v[j] : 0.0f;
+          }
+        }
+        // columns past n_dim are written as zeros so that the next pass can consume k in groups of 4
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (c0 + j < ld) out[rl * ld + c0 + j] = v[j];
+          if (store && c0 + j < p.n_dim) gout[c0 + j] = v[j];
+        }
+      }
+      TL(8 + q * 8 + 4);
+      const int done_pass = cur.pass;
+      if (!more) break;
+      cur = nxt;
+      more = next_chunk(a, nxt);
+      ++q;
+      if (cur.pass != done_pass) { float* t = in; in = out; out = t; }
+      __syncthreads();       // the old chunk buffer and activation tile are free; the new tile is visible
+    }
+  }
+
+  TL(2);
   const float t_log = block_sum(s_log, scratch);
   const float t_sq = block_sum(s_sq, scratch);
-  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-  if (threadIdx.x == 0) {
-    n.partial[((int64_t)e * n.tiles_cap + tile) * 2 + 0] = t_log;
-    n.partial[((int64_t)e * n.tiles_cap + tile) * 2 + 1] = t_sq;
+  if (tid == 0) {
+    a.partial[((int64_t)e * a.tiles_cap + blockIdx.x) * 2 + 0] = t_log;
+    a.partial[((int64_t)e * a.tiles_cap + blockIdx.x) * 2 + 1] = t_sq;
   }
-  if (!n.train) return;
+  if (!a.train) return;
   // the last CTA to arrive adds the partials in a fixed order and prepares the update
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     __threadfence();
-    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
-    last = (atomicAdd(&st->nll_ticket, 1u) == total - 1);
+    last = (atomicAdd(&st->nll_ticket, 1u) == gridDim.x * gridDim.y - 1);
   }
   __syncthreads();
-  if (!last || threadIdx.x >= 32) return;
+  if (!last || tid >= 32) return;
   __threadfence();
-  const int lane = threadIdx.x;
-  const int tiles = ((rows + kRowsF - 1) / kRowsF) * gridDim.x;
-  const float denom = (float)rows * (float)O;
+  const int tiles = (rows + kRows - 1) / kRows;
+  const float denom = (float)rows * (float)a.out_dim;
   float loss = 0.0f;
   for (int m = 0; m < a.ensemble; ++m) {
     float sl = 0.0f, sq = 0.0f;
-    for (int t = lane; t < tiles; t += 32) {
-      sl += __ldcg(&n.partial[((int64_t)m * n.tiles_cap + t) * 2 + 0]);
-      sq += __ldcg(&n.partial[((int64_t)m * n.tiles_cap + t) * 2 + 1]);
+    for (int t = tid; t < tiles; t += 32) {
+      sl += __ldcg(&a.partial[((int64_t)m * a.tiles_cap + t) * 2 + 0]);
+      sq += __ldcg(&a.partial[((int64_t)m * a.tiles_cap + t) * 2 + 1]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -297,12 +464,12 @@ train_head_nll_kernel(LayerArgs a, NllArgs n, OptParams opt, const FitDesc* desc
     }
     loss += (0.5f * (sl / denom) + 0.5f * (sq / denom)) / (float)a.ensemble;
   }
-  if (lane != 0) return;
+  if (tid != 0) return;
   const int it = st->iterations;
   const float t = (float)(it + 1);
   st->lr_t = schedule_lr(opt, it) * sqrtf(1.0f - powf(opt.beta2, t)) / (1.0f - powf(opt.beta1, t));
   st->loss = loss;
-  if (n.out_loss) *n.out_loss = loss;
+  if (a.out_loss) *a.out_loss = loss;
   if (desc != nullptr && desc->losses != nullptr) desc->losses[st->fit_step] = loss;
   st->nll_ticket = 0;
 }
@@ -329,122 +496,54 @@ __global__ void val_finalize_kernel(const double* acc, int ensemble, double deno
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward through one Dense + ReLU: dZ_{l-1} = (H_{l-1} > 0) * (dZ_l . W_l^T)
+// weight gradient + clip + Adam for every layer in one grid; also refreshes theta^T
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreadsF)
-train_backward_kernel(LayerArgs a, const FitDesc* desc, const TrainState* st, int rows_fixed) {
-  const int rows = resolve_rows(desc, st, rows_fixed);
-  const int e = blockIdx.z, r0 = blockIdx.y * kRowsF, k0 = blockIdx.x * kTileN;
-  if (r0 >= rows) return;
-  __shared__ float Zs[kRowsF][kChunk + 1];
-  __shared__ float Ws[kTileN][kChunk + 1];
-  const float* dZ = a.dz + e * a.dz_estride;
-  const float* W = a.theta + e * a.pn + a.off;
-  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
-  float acc[4] = {};
-  for (int n0 = 0; n0 < a.N; n0 += kChunk) {
-    const int nc = min(kChunk, a.N - n0);
-    if (n0) __syncthreads();
-    float zv[kRowsF * kChunk / kThreadsF];
-#pragma unroll
-    for (int j = 0; j < kRowsF * kChunk / kThreadsF; ++j) {
-      const int i = tid + j * kThreadsF, r = i >> 7, n = i & (kChunk - 1);
-      zv[j] = (r0 + r < rows && n < nc) ? __ldcg(dZ + (int64_t)(r0 + r) * a.N + n0 + n) : 0.0f;
-    }
-    if ((a.N & 3) == 0) {
-      float4 wv[kTileN * kChunk / 4 / kThreadsF];
-#pragma unroll
-      for (int j = 0; j < kTileN * kChunk / 4 / kThreadsF; ++j) {
-        const int i = tid + j * kThreadsF, k = i >> 5, n = (i & 31) * 4;
-        wv[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (k0 + k < a.K && n < nc)
-          wv[j] = __ldcg(reinterpret_cast<const float4*>(W + (int64_t)(k0 + k) * a.N + n0 + n));
-      }
-#pragma unroll
-      for (int j = 0; j < kTileN * kChunk / 4 / kThreadsF; ++j) {
-        const int i = tid + j * kThreadsF, k = i >> 5, n = (i & 31) * 4;
-        Ws[k][n] = wv[j].x; Ws[k][n + 1] = wv[j].y; Ws[k][n + 2] = wv[j].z; Ws[k][n + 3] = wv[j].w;
-      }
-    } else {
-      float wv[kTileN * kChunk / kThreadsF];
-#pragma unroll
-      for (int j = 0; j < kTileN * kChunk / kThreadsF; ++j) {
-        const int i = tid + j * kThreadsF, k = i >> 7, n = i & (kChunk - 1);
-        wv[j] = (k0 + k < a.K && n < nc) ? __ldcg(W + (int64_t)(k0 + k) * a.N + n0 + n) : 0.0f;
-      }
-#pragma unroll
-      for (int j = 0; j < kTileN * kChunk / kThreadsF; ++j) {
-        const int i = tid + j * kThreadsF;
-        Ws[i >> 7][i & (kChunk - 1)] = wv[j];
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < kRowsF * kChunk / kThreadsF; ++j) {
-      const int i = tid + j * kThreadsF;
-      Zs[i >> 7][i & (kChunk - 1)] = zv[j];
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int n = 0; n < nc; ++n) {
-      const float z = Zs[ty][n];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(z, Ws[tx * 4 + j][n], acc[j]);
-    }
-  }
-  const int r = r0 + ty;
-  if (r >= rows) return;
-  const float* H = a.in + e * a.in_estride + (int64_t)r * a.K;   // post-ReLU: > 0 <=> unit active
-  float* out = a.out + e * a.out_estride + (int64_t)r * a.K;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int k = k0 + tx * 4 + j;
-    if (k < a.K) out[k] = H[k] > 0.0f ? acc[j] : 0.0f;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// weight gradient + clip + Adam for every layer in one grid
-// ---------------------------------------------------------------------------------------------
-struct UpdTile { int layer, k0, n0; };
 struct UpdLayer {
   const float* h;       // input of the layer [E][rows][K]
   int64_t h_estride;
   const float* dz;      // [E][rows][N]
   int64_t dz_estride;
-  int off, K, N;
+  int64_t off, offT;    // offT < 0: no transposed copy (layer 0 is never back-propagated through)
+  int K, N;
   int gather_h;         // layer 0 inside fit: rows follow the batch index
+  int tile_begin;       // first tile index of this layer in the grid
+  int n_tiles_n;
 };
-constexpr int kMaxTrainLayers = 18;
 struct UpdArgs {
   UpdLayer layers[kMaxTrainLayers];
-  const UpdTile* tiles;
+  int n_layers;
   float* theta;
+  float* thetaT;
   float* m;
   float* v;
   float* grad;
-  int64_t pn;
+  int64_t pn, pnT;
   int ensemble;
 };
 
 __global__ void __launch_bounds__(kThreadsU)
 train_update_kernel(UpdArgs a, OptParams opt, const FitDesc* desc, TrainState* st, int rows_fixed) {
   const int rows = resolve_rows(desc, st, rows_fixed);
-  const UpdTile tile = a.tiles[blockIdx.x];
-  const UpdLayer& L = a.layers[tile.layer];
+  int li = 0;
+#pragma unroll 1
+  while (li + 1 < a.n_layers && (int)blockIdx.x >= a.layers[li + 1].tile_begin) ++li;
+  const UpdLayer& L = a.layers[li];
+  const int t_in = blockIdx.x - L.tile_begin;
+  const int tk0 = (t_in / L.n_tiles_n) * kTileU, tn0 = (t_in % L.n_tiles_n) * kTileU;
   const int e = blockIdx.y;
-  __shared__ float Hs[kRowsU][kTileN + 1];
-  __shared__ __align__(16) float Zs[kRowsU][kTileN];
+  __shared__ float Hs[kRowsU][kTileU + 1];
+  __shared__ __align__(16) float Zs[kRowsU][kTileU];
   const float* H = L.h + e * L.h_estride;
   const float* dZ = L.dz + e * L.dz_estride;
   const int* gidx = L.gather_h ? batch_rows_of(desc, st, e, a.ensemble) : nullptr;
   const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
   // the Adam operands are fetched while the gradient tile is being computed
-  const int k = tile.k0 + ty;
+  const int k = tk0 + ty;
   float th[4], mo[4], ve[4];
-  const int64_t p0 = e * a.pn + L.off + (int64_t)k * L.N + tile.n0 + tx * 4;
+  const int64_t p0 = e * a.pn + L.off + (int64_t)k * L.N + tn0 + tx * 4;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const bool ok = k <= L.K && tile.n0 + tx * 4 + j < L.N;
+    const bool ok = k <= L.K && tn0 + tx * 4 + j < L.N;
     th[j] = ok ? a.theta[p0 + j] : 0.0f;
     mo[j] = ok ? a.m[p0 + j] : 0.0f;
     ve[j] = ok ? a.v[p0 + j] : 0.0f;
@@ -452,25 +551,26 @@ train_update_kernel(UpdArgs a, OptParams opt, const FitDesc* desc, TrainState* s
   float acc[4] = {};
   for (int r0 = 0; r0 < rows; r0 += kRowsU) {
     if (r0) __syncthreads();
-    float hv[kRowsU * kTileN / kThreadsU], zv[kRowsU * kTileN / kThreadsU];
+    // every global load of the chunk is in flight before the first shared store
+    float hv[kRowsU * kTileU / kThreadsU], zv[kRowsU * kTileU / kThreadsU];
 #pragma unroll
-    for (int j = 0; j < kRowsU * kTileN / kThreadsU; ++j) {
+    for (int j = 0; j < kRowsU * kTileU / kThreadsU; ++j) {
       const int i = tid + j * kThreadsU, r = i >> 5, kk = i & 31;
       float h = 0.0f, z = 0.0f;
       if (r0 + r < rows) {
-        if (tile.k0 + kk < L.K) {
+        if (tk0 + kk < L.K) {
           const float* row = gidx ? desc->inputs + (int64_t)gidx[r0 + r] * L.K : H + (int64_t)(r0 + r) * L.K;
-          h = __ldcg(row + tile.k0 + kk);
-        } else if (tile.k0 + kk == L.K) {
+          h = __ldcg(row + tk0 + kk);
+        } else if (tk0 + kk == L.K) {
           h = 1.0f;                                   // the bias row
         }
-        if (tile.n0 + kk < L.N) z = __ldcg(dZ + (int64_t)(r0 + r) * L.N + tile.n0 + kk);
+        if (tn0 + kk < L.N) z = __ldcg(dZ + (int64_t)(r0 + r) * L.N + tn0 + kk);
       }
       hv[j] = h;
       zv[j] = z;
     }
 #pragma unroll
-    for (int j = 0; j < kRowsU * kTileN / kThreadsU; ++j) {
+    for (int j = 0; j < kRowsU * kTileU / kThreadsU; ++j) {
       const int i = tid + j * kThreadsU;
       Hs[i >> 5][i & 31] = hv[j];
       Zs[i >> 5][i & 31] = zv[j];
@@ -485,10 +585,11 @@ train_update_kernel(UpdArgs a, OptParams opt, const FitDesc* desc, TrainState* s
     }
   }
   const float lr_t = st->lr_t;
+  float nw[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   if (k <= L.K) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (tile.n0 + tx * 4 + j >= L.N) continue;
+      if (tn0 + tx * 4 + j >= L.N) continue;
       float g = acc[j];
       a.grad[p0 + j] = g;
       if (opt.clipvalue > 0.0f) g = fminf(fmaxf(g, -opt.clipvalue), opt.clipvalue);
@@ -496,7 +597,20 @@ train_update_kernel(UpdArgs a, OptParams opt, const FitDesc* desc, TrainState* s
       const float v = ve[j] + (1.0f - opt.beta2) * (g * g - ve[j]);
       a.m[p0 + j] = m;
       a.v[p0 + j] = v;
-      a.theta[p0 + j] = th[j] - lr_t * m / (sqrtf(v) + opt.epsilon);
+      nw[j] = th[j] - lr_t * m / (sqrtf(v) + opt.epsilon);
+      a.theta[p0 + j] = nw[j];
+    }
+  }
+  if (L.offT >= 0) {
+    // theta_l^T [N][K] for the chain kernel's back-propagation, written with unit stride along k
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Hs[tx * 4 + j][ty] = nw[j];          // Hs[n][k]
+    __syncthreads();
+    float* T = a.thetaT + e * a.pnT + L.offT;
+    for (int i = tid; i < kTileU * kTileU; i += kThreadsU) {
+      const int n = i >> 5, kk = i & 31;
+      if (tn0 + n < L.N && tk0 + kk < L.K) T[(int64_t)(tn0 + n) * L.K + tk0 + kk] = Hs[n][kk];
     }
   }
   // the last CTA advances optimizer.iterations and fit's step counter
@@ -525,8 +639,11 @@ struct simba_trainer {
   int E = 0, L = 0, U = 0, O = 0, IN = 0;
   int cap_rows = 0;
   int64_t pn = 0;
-  std::vector<int> off, K, N;        // train layers 0..L (L = merged head)
-  float *theta = nullptr, *m = nullptr, *v = nullptr, *grad = nullptr;
+  int64_t pnT = 0;
+  std::vector<int> off, offT, K, N;  // train layers 0..L (L = merged head); offT[0] = -1
+  float *theta = nullptr, *thetaT = nullptr, *m = nullptr, *v = nullptr, *grad = nullptr;
+  int ld_act = 0, aligned = 0;
+  size_t chain_smem = 0;
   std::vector<float*> act;           // act[l]: input of train layer l (act[0] = gathered x)
   std::vector<float*> dz;            // dz[l]: gradient w.r.t. the pre-activation of train layer l
   float* partial = nullptr;
@@ -534,7 +651,7 @@ struct simba_trainer {
   double* val_acc = nullptr;
   TrainState* state = nullptr;
   FitDesc* desc = nullptr;
-  UpdTile* upd_tiles = nullptr;
+  std::vector<int> tile_begin;       // update grid: first tile of each layer
   int n_upd_tiles = 0;
   cudaGraphExec_t fit_graph = nullptr;
   cudaStream_t graph_stream = nullptr;
@@ -606,11 +723,11 @@ extern "C" int simba_trainer_destroy(simba_trainer_t* t) {
   if (!t) return SIMBA_OK;
   if (t->fit_graph) cudaGraphExecDestroy(t->fit_graph);
   if (t->graph_stream) cudaStreamDestroy(t->graph_stream);
-  cudaFree(t->theta); cudaFree(t->m); cudaFree(t->v); cudaFree(t->grad);
+  cudaFree(t->theta); cudaFree(t->thetaT); cudaFree(t->m); cudaFree(t->v); cudaFree(t->grad);
   for (float* p : t->act) cudaFree(p);
   for (float* p : t->dz) cudaFree(p);
   cudaFree(t->partial); cudaFree(t->val_acc);
-  cudaFree(t->state); cudaFree(t->desc); cudaFree(t->upd_tiles);
+  cudaFree(t->state); cudaFree(t->desc);
   delete t;
   return SIMBA_OK;
 }
@@ -642,8 +759,19 @@ extern "C" int simba_trainer_create(simba_model_t* model, const simba_trainer_co
     const int N = l < t->L ? t->U : 2 * t->O;
     t->K.push_back(K); t->N.push_back(N); t->off.push_back((int)off);
     off += (int64_t)(K + 1) * N;
+    t->offT.push_back(l == 0 ? -1 : (int)t->pnT);
+    if (l > 0) t->pnT += (int64_t)N * K;
+    t->ld_act = std::max(t->ld_act, (std::max(K, N) + 3) & ~3);
   }
   t->pn = off;
+  t->aligned = (t->U % 4 == 0 && (2 * t->O) % 4 == 0) ? 1 : 0;
+  t->chain_smem = (size_t)(2 * kChunkK * kChunkN + (kChainThreads / 32) * kRows * kChunkN +
+                           2 * kRows * t->ld_act) * sizeof(float);
+  if (t->chain_smem > 220 * 1024) {
+    const int units = t->U;
+    delete t;
+    return set_error(SIMBA_ERR_UNSUPPORTED, "units %d: activation tiles do not fit shared memory", units);
+  }
   const int E = t->E;
   std::vector<float> host((size_t)E * t->pn);
   for (int e = 0; e < E; ++e) {
@@ -664,6 +792,20 @@ extern "C" int simba_trainer_create(simba_model_t* model, const simba_trainer_co
   TRY_OR_FREE(cudaMalloc(&t->v, pbytes));
   TRY_OR_FREE(cudaMalloc(&t->grad, pbytes));
   TRY_OR_FREE(cudaMemcpy(t->theta, host.data(), pbytes, cudaMemcpyHostToDevice));
+  {
+    std::vector<float> hostT((size_t)E * std::max<int64_t>(t->pnT, 1));
+    for (int e = 0; e < E; ++e)
+      for (int l = 1; l <= t->L; ++l) {
+        const float* W = host.data() + (size_t)e * t->pn + t->off[l];
+        float* T = hostT.data() + (size_t)e * t->pnT + t->offT[l];
+        for (int k = 0; k < t->K[l]; ++k)
+          for (int n = 0; n < t->N[l]; ++n) T[(size_t)n * t->K[l] + k] = W[(size_t)k * t->N[l] + n];
+      }
+    TRY_OR_FREE(cudaMalloc(&t->thetaT, hostT.size() * sizeof(float)));
+    TRY_OR_FREE(cudaMemcpy(t->thetaT, hostT.data(), hostT.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  TRY_OR_FREE(cudaFuncSetAttribute(train_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)t->chain_smem));
   TRY_OR_FREE(cudaMemset(t->m, 0, pbytes));
   TRY_OR_FREE(cudaMemset(t->v, 0, pbytes));
   TRY_OR_FREE(cudaMemset(t->grad, 0, pbytes));
@@ -674,56 +816,59 @@ extern "C" int simba_trainer_create(simba_model_t* model, const simba_trainer_co
     TRY_OR_FREE(cudaMalloc(&t->act[l], (size_t)E * R * t->K[l] * sizeof(float)));
     TRY_OR_FREE(cudaMalloc(&t->dz[l], (size_t)E * cfg->batch_size * t->N[l] * sizeof(float)));
   }
-  t->tiles_cap = (int)((R + kRowsF - 1) / kRowsF) * ((2 * t->O + kTileN - 1) / kTileN);
+  t->tiles_cap = (int)((R + kRows - 1) / kRows);
   TRY_OR_FREE(cudaMalloc(&t->partial, (size_t)E * t->tiles_cap * 2 * sizeof(float)));
   TRY_OR_FREE(cudaMalloc(&t->val_acc, (size_t)E * 2 * sizeof(double)));
   TRY_OR_FREE(cudaMalloc(&t->state, sizeof(TrainState)));
   TRY_OR_FREE(cudaMemset(t->state, 0, sizeof(TrainState)));
   TRY_OR_FREE(cudaMalloc(&t->desc, sizeof(FitDesc)));
   TRY_OR_FREE(cudaMemset(t->desc, 0, sizeof(FitDesc)));
-  std::vector<UpdTile> tiles;
-  for (int l = 0; l <= t->L; ++l)
-    for (int k0 = 0; k0 <= t->K[l]; k0 += kTileN)
-      for (int n0 = 0; n0 < t->N[l]; n0 += kTileN) tiles.push_back({l, k0, n0});
-  t->n_upd_tiles = (int)tiles.size();
-  TRY_OR_FREE(cudaMalloc(&t->upd_tiles, tiles.size() * sizeof(UpdTile)));
-  TRY_OR_FREE(cudaMemcpy(t->upd_tiles, tiles.data(), tiles.size() * sizeof(UpdTile),
-                         cudaMemcpyHostToDevice));
+  for (int l = 0; l <= t->L; ++l) {
+    t->tile_begin.push_back(t->n_upd_tiles);
+    t->n_upd_tiles += ((t->K[l] + 1 + kTileU - 1) / kTileU) * ((t->N[l] + kTileU - 1) / kTileU);
+  }
 #undef TRY_OR_FREE
-  t->launches_per_step = 2 * t->L + 2;
+  t->launches_per_step = 2;
   *out = t;
   return SIMBA_OK;
 }
 
-// one launch per hidden layer, then the head fused with the likelihood. x may be shared by the
-// members (estride 0, validation) or gathered through the fit descriptor (gather = 1).
-static int enqueue_forward(simba_trainer_t* t, const float* x, int64_t x_estride, const float* y,
-                           int64_t y_estride, int gather, int grid_rows, int rows_fixed,
-                           const FitDesc* desc, int train, float* out_loss, cudaStream_t s) {
-  const int64_t R = t->cap_rows;
-  const int row_tiles = (grid_rows + kRowsF - 1) / kRowsF;
+// the chain kernel: forward + likelihood (+ back-propagation of the activations when `train`).
+// x may be shared by the members (estride 0, validation) or gathered through the fit descriptor.
+static int enqueue_chain(simba_trainer_t* t, const float* x, int64_t x_estride, const float* y,
+                         int64_t y_estride, int gather, int grid_rows, int rows_fixed,
+                         const FitDesc* desc, int train, float* out_loss, cudaStream_t s) {
+  const int64_t R = t->cap_rows, B = t->cfg.batch_size;
+  ChainArgs a{};
+  int np = 0;
   for (int l = 0; l <= t->L; ++l) {
-    LayerArgs a{};
-    a.in = l == 0 ? x : t->act[l];
-    a.in_estride = l == 0 ? x_estride : R * t->K[l];
-    a.gather_in = l == 0 ? gather : 0;
-    a.theta = t->theta; a.pn = t->pn; a.off = t->off[l]; a.K = t->K[l]; a.N = t->N[l];
-    a.ensemble = t->E;
-    dim3 grid((a.N + kTileN - 1) / kTileN, row_tiles, t->E);
-    if (l < t->L) {
-      a.out = t->act[l + 1];
-      a.out_estride = R * t->N[l];
-      train_forward_kernel<<<grid, kThreadsF, 0, s>>>(a, desc, t->state, rows_fixed);
-    } else {
-      NllArgs n{};
-      n.y = y; n.y_estride = y_estride; n.gather_y = gather;
-      n.d_raw = train ? t->dz[t->L] : nullptr;
-      n.d_estride = (int64_t)t->cfg.batch_size * 2 * t->O;
-      n.partial = t->partial; n.tiles_cap = t->tiles_cap;
-      n.out_dim = t->O; n.train = train; n.out_loss = out_loss;
-      train_head_nll_kernel<<<grid, kThreadsF, 0, s>>>(a, n, opt_params(t), desc, t->state, rows_fixed);
-    }
+    ChainPass& p = a.pass[np++];
+    p.w_off = t->off[l];
+    p.bias_off = t->off[l] + (int64_t)t->K[l] * t->N[l];
+    p.k_dim = t->K[l]; p.n_dim = t->N[l];
+    p.kind = l < t->L ? kPassHidden : kPassHead;
+    p.out = l < t->L ? t->act[l + 1] : t->dz[l];
+    p.out_estride = l < t->L ? R * t->N[l] : B * t->N[l];
   }
+  a.n_forward = np;
+  if (train)
+    for (int l = t->L; l >= 1; --l) {
+      ChainPass& p = a.pass[np++];
+      p.w_off = t->offT[l];
+      p.k_dim = t->N[l]; p.n_dim = t->K[l];
+      p.kind = kPassBackward;
+      p.out = t->dz[l - 1]; p.out_estride = B * t->K[l];      // K_l == N_{l-1}
+      p.mask = t->act[l]; p.mask_estride = R * t->K[l];
+    }
+  a.n_pass = np;
+  a.x = x; a.x_estride = x_estride; a.gather = gather;
+  a.y = y; a.y_estride = y_estride;
+  a.theta = t->theta; a.thetaT = t->thetaT; a.pn = t->pn; a.pnT = t->pnT;
+  a.ld_act = t->ld_act; a.out_dim = t->O; a.ensemble = t->E; a.aligned = t->aligned;
+  a.partial = t->partial; a.tiles_cap = t->tiles_cap; a.train = train; a.out_loss = out_loss;
+  dim3 grid((grid_rows + kRows - 1) / kRows, t->E);
+  train_chain_kernel<<<grid, kChainThreads, t->chain_smem, s>>>(a, opt_params(t), desc, t->state,
+                                                                rows_fixed);
   SIMBA_CUDA_TRY(cudaGetLastError());
   return SIMBA_OK;
 }
@@ -734,31 +879,24 @@ static int enqueue_step(simba_trainer_t* t, const float* x, int64_t x_estride, c
   const int64_t R = t->cap_rows, B = t->cfg.batch_size;
   const int gather = desc ? 1 : 0;
   const int grid_rows = desc ? t->cfg.batch_size : rows_fixed;
-  int rc = enqueue_forward(t, x, x_estride, y, y_estride, gather, grid_rows, rows_fixed, desc, 1,
-                           out_loss, s);
+  int rc = enqueue_chain(t, x, x_estride, y, y_estride, gather, grid_rows, rows_fixed, desc, 1,
+                         out_loss, s);
   if (rc) return rc;
-  const int row_tiles = (grid_rows + kRowsF - 1) / kRowsF;
-  for (int l = t->L; l >= 1; --l) {
-    LayerArgs a{};
-    a.in = t->act[l]; a.in_estride = R * t->K[l];       // H_{l-1}: the (ReLU) input of layer l
-    a.theta = t->theta; a.pn = t->pn; a.off = t->off[l]; a.K = t->K[l]; a.N = t->N[l];
-    a.dz = t->dz[l]; a.dz_estride = B * t->N[l];
-    a.out = t->dz[l - 1]; a.out_estride = B * t->N[l - 1];   // N_{l-1} == K_l
-    a.ensemble = t->E;
-    dim3 grid((a.K + kTileN - 1) / kTileN, row_tiles, t->E);
-    train_backward_kernel<<<grid, kThreadsF, 0, s>>>(a, desc, t->state, rows_fixed);
-  }
   UpdArgs u{};
   for (int l = 0; l <= t->L; ++l) {
-    u.layers[l].h = l == 0 ? x : t->act[l];
-    u.layers[l].h_estride = l == 0 ? x_estride : R * t->K[l];
-    u.layers[l].gather_h = l == 0 ? gather : 0;
-    u.layers[l].dz = t->dz[l];
-    u.layers[l].dz_estride = B * t->N[l];
-    u.layers[l].off = t->off[l]; u.layers[l].K = t->K[l]; u.layers[l].N = t->N[l];
+    UpdLayer& U = u.layers[l];
+    U.h = l == 0 ? x : t->act[l];
+    U.h_estride = l == 0 ? x_estride : R * t->K[l];
+    U.gather_h = l == 0 ? gather : 0;
+    U.dz = t->dz[l];
+    U.dz_estride = B * t->N[l];
+    U.off = t->off[l]; U.offT = t->offT[l]; U.K = t->K[l]; U.N = t->N[l];
+    U.tile_begin = t->tile_begin[l];
+    U.n_tiles_n = (t->N[l] + kTileU - 1) / kTileU;
   }
-  u.tiles = t->upd_tiles; u.theta = t->theta; u.m = t->m; u.v = t->v; u.grad = t->grad; u.pn = t->pn;
-  u.ensemble = t->E;
+  u.n_layers = t->L + 1;
+  u.theta = t->theta; u.thetaT = t->thetaT; u.m = t->m; u.v = t->v; u.grad = t->grad;
+  u.pn = t->pn; u.pnT = t->pnT; u.ensemble = t->E;
   train_update_kernel<<<dim3(t->n_upd_tiles, t->E), kThreadsU, 0, s>>>(u, opt_params(t), desc,
                                                                         t->state, rows_fixed);
   SIMBA_CUDA_TRY(cudaGetLastError());
@@ -810,9 +948,9 @@ extern "C" int simba_trainer_validation(simba_trainer_t* t, const float* x, cons
   cudaStream_t s = (cudaStream_t)stream;
   for (int64_t r0 = 0; r0 < rows; r0 += t->cap_rows) {
     const int nr = (int)((rows - r0) < t->cap_rows ? (rows - r0) : t->cap_rows);
-    int rc = enqueue_forward(t, x + r0 * t->IN, 0, y + r0 * t->O, 0, 0, nr, nr, nullptr, 0, nullptr, s);
+    int rc = enqueue_chain(t, x + r0 * t->IN, 0, y + r0 * t->O, 0, 0, nr, nr, nullptr, 0, nullptr, s);
     if (rc) return rc;
-    const int tiles = ((nr + kRowsF - 1) / kRowsF) * ((2 * t->O + kTileN - 1) / kTileN);
+    const int tiles = (nr + kRows - 1) / kRows;
     val_accumulate_kernel<<<1, 32, 0, s>>>(t->partial, t->tiles_cap, tiles, t->E, t->val_acc,
                                            r0 == 0 ? 1 : 0);
   }
@@ -862,6 +1000,14 @@ extern "C" int64_t simba_trainer_iterations(simba_trainer_t* t) {
   if (cudaMemcpy(&st, t->state, sizeof(st), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return st.iterations;
 }
+
+#ifdef SIMBA_TRAIN_TIMELINE
+extern "C" int simba_debug_train_timeline(long long* out) {
+  SIMBA_CUDA_TRY(cudaDeviceSynchronize());
+  SIMBA_CUDA_TRY(cudaMemcpyFromSymbol(out, g_train_tl, sizeof(long long) * 512));
+  return SIMBA_OK;
+}
+#endif
 
 extern "C" int simba_trainer_launches_per_step(simba_trainer_t* t) {
   return t ? t->launches_per_step : 0;
