@@ -6,7 +6,7 @@
 // Shape of the work: E members x batch 64 x a 4x128 MLP is 28 MFLOP per member-step — nothing a
 // launch can hide — so the step is latency-bound and the design minimises dependent launches and
 // dependent memory round trips. Forward and back-propagation of the activations are ROW-LOCAL
-// (row r of every H_l and dZ_l depends only on row r of the batch), so one CTA walks a 16-row
+// (row r of every H_l and dZ_l depends only on row r of the batch), so one CTA walks an 8-row
 // tile through the whole chain without any inter-CTA dependency:
 //   chain   1 launch   H_{l+1} = relu([H_l, 1] . theta_l), l < L; head -> (mu, var) -> likelihood,
 //                      d(mu), d(raw var), lr_t; then dZ_{l-1} = relu'(H_l) * (dZ_l . theta_l^T),
@@ -36,14 +36,18 @@ using namespace simba;
 
 namespace {
 
-constexpr int kRows = 16;        // batch rows per chain CTA
-constexpr int kChunkK = 64;      // weight chunk: [64 k] x [128 n] fp32 = 32 KB, two in flight
+constexpr int kRows = 8;         // batch rows per chain CTA (64-row batch x 5 members -> 40 CTAs)
+constexpr int kChunkK = 128;     // weight chunk: [128 k] x [128 n] fp32 = 64 KB, two in flight
 constexpr int kChunkN = 128;
 constexpr int kChainThreads = 256;
+constexpr int kSplitK = 4;       // warps 0-3: first half of the rows, warps 4-7: second half; 4-way split-K
+constexpr int kHalfRows = kRows / 2;
+constexpr int kEpiRows = kRows / 8;   // epilogue rows per warp
 constexpr int kTileU = 32;       // update kernel: [32 k] x [32 n] tile of dtheta
 constexpr int kRowsU = 64;       // update kernel: batch rows per staged chunk
 constexpr int kThreadsU = 256;
 constexpr int kMaxTrainLayers = 18;
+constexpr int kGraphSteps = 16;  // fit(): steps per CUDA-graph launch
 
 struct TrainState {
   int iterations;        // optimizer.iterations
@@ -51,7 +55,6 @@ struct TrainState {
   float lr_t;            // lr(iterations) * sqrt(1 - beta2^t) / (1 - beta1^t) of the current step
   float loss;
   unsigned nll_ticket;
-  unsigned upd_ticket;
 };
 
 struct FitDesc {
@@ -68,16 +71,25 @@ struct OptParams {
   int schedule, steps_per_epoch, train_epochs;
 };
 
-__device__ __forceinline__ int resolve_rows(const FitDesc* desc, const TrainState* st, int rows_fixed) {
-  if (desc != nullptr && desc->batch_rows != nullptr) return desc->batch_rows[st->fit_step];
+// A captured graph holds several consecutive steps: step i of the graph works at
+// (st->fit_step + i, st->iterations + i) and one single-thread kernel advances the counters at
+// the end of the graph, so no kernel of the step needs a grid-wide "last CTA" handshake for it.
+__device__ __forceinline__ int resolve_rows(const FitDesc* desc, const TrainState* st, int rows_fixed,
+                                            int step_off) {
+  if (desc != nullptr && desc->batch_rows != nullptr) return desc->batch_rows[st->fit_step + step_off];
   return rows_fixed;
 }
 
 // fit(): `train_inputs[shuffles_per_mlp]` (mlp_ensemble.py:175-176) is never materialised — the
 // kernels that read the batch follow the index
 __device__ __forceinline__ const int* batch_rows_of(const FitDesc* desc, const TrainState* st, int e,
-                                                    int ensemble) {
-  return desc->batch_index + ((int64_t)st->fit_step * ensemble + e) * desc->bmax;
+                                                    int ensemble, int step_off) {
+  return desc->batch_index + ((int64_t)(st->fit_step + step_off) * ensemble + e) * desc->bmax;
+}
+
+__global__ void advance_kernel(TrainState* st, int n) {
+  st->iterations += n;
+  st->fit_step += n;
 }
 
 __global__ void set_fit_desc_kernel(FitDesc d, FitDesc* out, TrainState* st) {
@@ -249,25 +261,29 @@ __device__ __forceinline__ void issue_chunk(const ChainArgs& a, const ChunkCurso
   }
 }
 
-// The multiply is split-K across the 8 warps: warp w owns k-groups w, w + 8, ... of the chunk and
-// accumulates a full [16 x 128] partial tile in registers (lane -> 4 columns, 16 rows: 64
-// accumulators), so every weight element is read from shared memory exactly once per CTA and the
-// 64 independent FMA chains hide the shared-memory latency. The 8 partial tiles are added in warp
-// order through shared memory when the layer's last chunk is done.
+// The multiply: warps 0-3 own the first half of the tile's rows and warps 4-7 the second; within
+// a half the four warps split K (warp s takes k-groups s, s + 4, ...). A lane owns 4 columns, so
+// a thread accumulates a [kHalfRows x 4] register tile of independent FMA chains, and the
+// operands of a k-group (4 weight float4s + kHalfRows broadcast activation float4s) sit in
+// registers ahead of their use. The four partial tiles of a half are added in a fixed order
+// through shared memory when the layer's last chunk is done.
 __global__ void __launch_bounds__(kChainThreads)
-train_chain_kernel(ChainArgs a, OptParams opt, const FitDesc* desc, TrainState* st, int rows_fixed) {
+train_chain_kernel(ChainArgs a, OptParams opt, const FitDesc* desc, TrainState* st, int rows_fixed,
+                   int step_off) {
   extern __shared__ __align__(16) float smem[];
-  float* red = smem + 2 * kChunkK * kChunkN;                 // [8 warps][16][128]
-  float* act0 = red + (kChainThreads / 32) * kRows * kChunkN;
+  float* red = smem + 2 * kChunkK * kChunkN;                 // [2 halves][4 k-slices][8][128]
+  float* act0 = red + 2 * kSplitK * kHalfRows * kChunkN;
   float* act1 = act0 + kRows * a.ld_act;
   __shared__ float scratch[kChainThreads / 32];
   __shared__ __align__(8) unsigned long long bars[2];
   __shared__ bool last;
 
-  const int rows = resolve_rows(desc, st, rows_fixed);
+  const int rows = resolve_rows(desc, st, rows_fixed, step_off);
   const int e = blockIdx.y, r0 = blockIdx.x * kRows;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rl = tid >> 4, cl = 8 * (tid & 15);     // epilogue: row rl, chunk-local columns cl .. cl + 7
+  const int half = warp >> 2, kslice = warp & 3;    // multiply: rows 8 half .. 8 half + 7
+  const int cl = 4 * lane;                          // chunk-local columns cl .. cl + 3 (both phases)
+  // epilogue: warp w finishes rows kEpiRows * w .. of the tile
   const int ld = a.ld_act;
   float s_log = 0.0f, s_sq = 0.0f;
   TL(0);
@@ -285,7 +301,7 @@ train_chain_kernel(ChainArgs a, OptParams opt, const FitDesc* desc, TrainState* 
     // the batch tile (layer 0 input), zero-padded to a multiple of 4 columns
     {
       const int K0 = a.pass[0].k_dim, K0r = (K0 + 3) & ~3;
-      const int* gidx = a.gather ? batch_rows_of(desc, st, e, a.ensemble) : nullptr;
+      const int* gidx = a.gather ? batch_rows_of(desc, st, e, a.ensemble, step_off) : nullptr;
       const float* X = a.x + e * a.x_estride;
       for (int i = tid; i < kRows * K0r; i += kChainThreads) {
         const int r = i / K0r, k = i - r * K0r;
@@ -300,7 +316,7 @@ train_chain_kernel(ChainArgs a, OptParams opt, const FitDesc* desc, TrainState* 
     __syncthreads();
     float* in = act0;
     float* out = act1;
-    float acc[kRows][4] = {};
+    float acc[kHalfRows][4] = {};
     int q = 0;
     TL(1);
     while (true) {
@@ -314,31 +330,32 @@ train_chain_kernel(ChainArgs a, OptParams opt, const FitDesc* desc, TrainState* 
       const int kc4 = (kc + 3) & ~3;
       const bool last_k = cur.k0 + kChunkK >= p.k_dim;
       const int c0 = cur.n0 + cl;
-      const int r = r0 + rl;
-      const bool row_ok = r < rows;
       // epilogue operands are requested before the multiply so their latency hides behind it
-      float pb[8] = {};                              // bias (forward / head)
-      float pm[8] = {};                              // backward: H_l (mask); head: targets at even j
+      float pb[4] = {};                              // bias (forward / head)
+      float pm[kEpiRows][4] = {};                    // backward: H_l (mask); head: targets at even j
       if (last_k) {
         if (p.kind != kPassBackward) {
           const float* bias = a.theta + e * a.pn + p.bias_off;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
+          for (int j = 0; j < 4; ++j)
             if (c0 + j < p.n_dim) pb[j] = __ldcg(bias + c0 + j);
         }
-        if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < kEpiRows; ++i) {
+          const int r = r0 + kEpiRows * warp + i;
+          if (r >= rows) continue;
           if (p.kind == kPassBackward) {
             const float* h = p.mask + e * p.mask_estride + (int64_t)r * p.n_dim;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (c0 + j < p.n_dim) pm[j] = __ldcg(h + c0 + j);
+            for (int j = 0; j < 4; ++j)
+              if (c0 + j < p.n_dim) pm[i][j] = __ldcg(h + c0 + j);
           } else if (p.kind == kPassHead) {
             const float* y = a.gather
-                ? desc->targets + (int64_t)batch_rows_of(desc, st, e, a.ensemble)[r] * a.out_dim
+                ? desc->targets + (int64_t)batch_rows_of(desc, st, e, a.ensemble, step_off)[r] * a.out_dim
                 : a.y + e * a.y_estride + (int64_t)r * a.out_dim;
 #pragma unroll
-            for (int j = 0; j < 8; j += 2)
-              if (c0 + j < p.n_dim) pm[j] = __ldg(y + ((c0 + j) >> 1));
+            for (int j = 0; j < 4; j += 2)
+              if (c0 + j < p.n_dim) pm[i][j] = __ldg(y + ((c0 + j) >> 1));
           }
         }
       }
@@ -346,79 +363,105 @@ train_chain_kernel(ChainArgs a, OptParams opt, const FitDesc* desc, TrainState* 
       TL(8 + q * 8 + 2);
       {
         const int S = chunk_stride(a, p);
-        const float* w = wb + 4 * lane;
-        const float* xin = in + cur.k0;
-        for (int kk = 4 * warp; kk < kc4; kk += 4 * (kChainThreads / 32)) {
+        const float* w = wb + cl;
+        const float* xin = in + (half * kHalfRows) * ld + cur.k0;
+        for (int kk = 4 * kslice; kk < kc4; kk += 4 * kSplitK) {
           const float4 w0 = *reinterpret_cast<const float4*>(w + (kk + 0) * S);
           const float4 w1 = *reinterpret_cast<const float4*>(w + (kk + 1) * S);
           const float4 w2 = *reinterpret_cast<const float4*>(w + (kk + 2) * S);
           const float4 w3 = *reinterpret_cast<const float4*>(w + (kk + 3) * S);
+          float4 x[kHalfRows];
 #pragma unroll
-          for (int i = 0; i < kRows; ++i) {
-            const float4 x = *reinterpret_cast<const float4*>(xin + i * ld + kk);
-            acc[i][0] = fmaf(x.x, w0.x, acc[i][0]); acc[i][1] = fmaf(x.x, w0.y, acc[i][1]);
-            acc[i][2] = fmaf(x.x, w0.z, acc[i][2]); acc[i][3] = fmaf(x.x, w0.w, acc[i][3]);
-            acc[i][0] = fmaf(x.y, w1.x, acc[i][0]); acc[i][1] = fmaf(x.y, w1.y, acc[i][1]);
-            acc[i][2] = fmaf(x.y, w1.z, acc[i][2]); acc[i][3] = fmaf(x.y, w1.w, acc[i][3]);
-            acc[i][0] = fmaf(x.z, w2.x, acc[i][0]); acc[i][1] = fmaf(x.z, w2.y, acc[i][1]);
-            acc[i][2] = fmaf(x.z, w2.z, acc[i][2]); acc[i][3] = fmaf(x.z, w2.w, acc[i][3]);
-            acc[i][0] = fmaf(x.w, w3.x, acc[i][0]); acc[i][1] = fmaf(x.w, w3.y, acc[i][1]);
-            acc[i][2] = fmaf(x.w, w3.z, acc[i][2]); acc[i][3] = fmaf(x.w, w3.w, acc[i][3]);
+          for (int i = 0; i < kHalfRows; ++i) x[i] = *reinterpret_cast<const float4*>(xin + i * ld + kk);
+#pragma unroll
+          for (int i = 0; i < kHalfRows; ++i) {
+            acc[i][0] = fmaf(x[i].x, w0.x, acc[i][0]); acc[i][1] = fmaf(x[i].x, w0.y, acc[i][1]);
+            acc[i][2] = fmaf(x[i].x, w0.z, acc[i][2]); acc[i][3] = fmaf(x[i].x, w0.w, acc[i][3]);
+          }
+#pragma unroll
+          for (int i = 0; i < kHalfRows; ++i) {
+            acc[i][0] = fmaf(x[i].y, w1.x, acc[i][0]); acc[i][1] = fmaf(x[i].y, w1.y, acc[i][1]);
+            acc[i][2] = fmaf(x[i].y, w1.z, acc[i][2]); acc[i][3] = fmaf(x[i].y, w1.w, acc[i][3]);
+          }
+#pragma unroll
+          for (int i = 0; i < kHalfRows; ++i) {
+            acc[i][0] = fmaf(x[i].z, w2.x, acc[i][0]); acc[i][1] = fmaf(x[i].z, w2.y, acc[i][1]);
+            acc[i][2] = fmaf(x[i].z, w2.z, acc[i][2]); acc[i][3] = fmaf(x[i].z, w2.w, acc[i][3]);
+          }
+#pragma unroll
+          for (int i = 0; i < kHalfRows; ++i) {
+            acc[i][0] = fmaf(x[i].w, w3.x, acc[i][0]); acc[i][1] = fmaf(x[i].w, w3.y, acc[i][1]);
+            acc[i][2] = fmaf(x[i].w, w3.z, acc[i][2]); acc[i][3] = fmaf(x[i].w, w3.w, acc[i][3]);
           }
         }
       }
       TL(8 + q * 8 + 3);
       if (last_k) {
-        // add the 8 warps' partial tiles in warp order, then the epilogue of row rl, columns c0..c0+7
+        // add the four k-slices of each half in slice order, then the epilogue of this warp's rows,
+        // columns c0 .. c0 + 3
 #pragma unroll
-        for (int i = 0; i < kRows; ++i) {
-          *reinterpret_cast<float4*>(red + (warp * kRows + i) * kChunkN + 4 * lane) =
+        for (int i = 0; i < kHalfRows; ++i) {
+          *reinterpret_cast<float4*>(red + ((half * kSplitK + kslice) * kHalfRows + i) * kChunkN + cl) =
               make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
           acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
         }
         __syncthreads();
-        float v[8] = {};
 #pragma unroll
-        for (int w8 = 0; w8 < kChainThreads / 32; ++w8) {
-          const float4 lo = *reinterpret_cast<const float4*>(red + (w8 * kRows + rl) * kChunkN + cl);
-          const float4 hi = *reinterpret_cast<const float4*>(red + (w8 * kRows + rl) * kChunkN + cl + 4);
-          v[0] += lo.x; v[1] += lo.y; v[2] += lo.z; v[3] += lo.w;
-          v[4] += hi.x; v[5] += hi.y; v[6] += hi.z; v[7] += hi.w;
-        }
-        float* gout = p.out + e * p.out_estride + (int64_t)r * p.n_dim;
-        const bool store = row_ok && (p.kind != kPassHead || a.train);
-        if (p.kind == kPassHead) {
-          const float c = 1.0f / ((float)rows * (float)a.out_dim * (float)a.ensemble);
+        for (int i = 0; i < kEpiRows; ++i) {
+          const int rl = kEpiRows * warp + i, r = r0 + rl;
+          const bool row_ok = r < rows;
+          float v[4] = {};
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            float d_mu = 0.0f, d_pre = 0.0f;
-            if (c0 + j < p.n_dim && row_ok) {
-              const float mu = v[j] + pb[j];
-              const float pre = v[j + 1] + pb[j + 1];
-              const float var = softplus_tf(pre) + 1e-4f;
-              const float diff = mu - pm[j];
-              const float inv = 1.0f / var;
-              s_log += logf(6.28318530717958647692f * var);
-              s_sq += diff * diff * inv;
-              d_mu = c * diff * inv;
-              d_pre = 0.5f * c * (inv - diff * diff * inv * inv) * (1.0f / (1.0f + expf(-pre)));
+          for (int sl = 0; sl < kSplitK; ++sl) {
+            const float4 pv = *reinterpret_cast<const float4*>(
+                red + (((rl / kHalfRows) * kSplitK + sl) * kHalfRows + (rl % kHalfRows)) * kChunkN + cl);
+            v[0] += pv.x; v[1] += pv.y; v[2] += pv.z; v[3] += pv.w;
+          }
+          if (p.kind == kPassHead) {
+            const float c = 1.0f / ((float)rows * (float)a.out_dim * (float)a.ensemble);
+#pragma unroll
+            for (int j = 0; j < 4; j += 2) {
+              float d_mu = 0.0f, d_pre = 0.0f;
+              if (c0 + j < p.n_dim && row_ok) {
+                const float mu = v[j] + pb[j];
+                const float pre = v[j + 1] + pb[j + 1];
+                const float var = softplus_tf(pre) + 1e-4f;
+                const float diff = mu - pm[i][j];
+                const float inv = 1.0f / var;
+                s_log += logf(6.28318530717958647692f * var);
+                s_sq += diff * diff * inv;
+                d_mu = c * diff * inv;
+                d_pre = 0.5f * c * (inv - diff * diff * inv * inv) * (1.0f / (1.0f + expf(-pre)));
+              }
+              v[j] = d_mu;
+              v[j + 1] = d_pre;
             }
-            v[j] = d_mu;
-            v[j + 1] = d_pre;
-          }
-        } else {
+          } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const bool ok = c0 + j < p.n_dim;
-            if (p.kind == kPassHidden) v[j] = ok ? fmaxf(v[j] + pb[j], 0.0f) : 0.0f;
-            else v[j] = (ok && row_ok && pm[j] > 0.0f) ? v[j] : 0.0f;
+            for (int j = 0; j < 4; ++j) {
+              const bool ok = c0 + j < p.n_dim;
+              if (p.kind == kPassHidden) v[j] = ok ? fmaxf(v[j] + pb[j], 0.0f) : 0.0f;
+              else v[j] = (ok && row_ok && pm[i][j] > 0.0f) ? v[j] : 0.0f;
+            }
           }
-        }
-        // columns past n_dim are written as zeros so that the next pass can consume k in groups of 4
+          // columns past n_dim are written as zeros so that the next pass can consume k in groups of 4
+          if (c0 + 3 < ld) {
+            *reinterpret_cast<float4*>(out + rl * ld + c0) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (c0 + j < ld) out[rl * ld + c0 + j] = v[j];
-          if (store && c0 + j < p.n_dim) gout[c0 + j] = v[j];
+            for (int j = 0; j < 4; ++j)
+              if (c0 + j < ld) out[rl * ld + c0 + j] = v[j];
+          }
+          if (row_ok && (p.kind != kPassHead || a.train)) {
+            float* gout = p.out + e * p.out_estride + (int64_t)r * p.n_dim + c0;
+            if (a.aligned && c0 + 3 < p.n_dim) {
+              *reinterpret_cast<float4*>(gout) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (c0 + j < p.n_dim) gout[j] = v[j];
+            }
+          }
         }
       }
       TL(8 + q * 8 + 4);
@@ -465,12 +508,12 @@ train_chain_kernel(ChainArgs a, OptParams opt, const FitDesc* desc, TrainState* 
     loss += (0.5f * (sl / denom) + 0.5f * (sq / denom)) / (float)a.ensemble;
   }
   if (tid != 0) return;
-  const int it = st->iterations;
+  const int it = st->iterations + step_off;
   const float t = (float)(it + 1);
   st->lr_t = schedule_lr(opt, it) * sqrtf(1.0f - powf(opt.beta2, t)) / (1.0f - powf(opt.beta1, t));
   st->loss = loss;
   if (a.out_loss) *a.out_loss = loss;
-  if (desc != nullptr && desc->losses != nullptr) desc->losses[st->fit_step] = loss;
+  if (desc != nullptr && desc->losses != nullptr) desc->losses[st->fit_step + step_off] = loss;
   st->nll_ticket = 0;
 }
 
@@ -522,8 +565,9 @@ struct UpdArgs {
 };
 
 __global__ void __launch_bounds__(kThreadsU)
-train_update_kernel(UpdArgs a, OptParams opt, const FitDesc* desc, TrainState* st, int rows_fixed) {
-  const int rows = resolve_rows(desc, st, rows_fixed);
+train_update_kernel(UpdArgs a, OptParams opt, const FitDesc* desc, const TrainState* st, int rows_fixed,
+                    int step_off) {
+  const int rows = resolve_rows(desc, st, rows_fixed, step_off);
   int li = 0;
 #pragma unroll 1
   while (li + 1 < a.n_layers && (int)blockIdx.x >= a.layers[li + 1].tile_begin) ++li;
@@ -535,7 +579,7 @@ train_update_kernel(UpdArgs a, OptParams opt, const FitDesc* desc, TrainState* s
   __shared__ __align__(16) float Zs[kRowsU][kTileU];
   const float* H = L.h + e * L.h_estride;
   const float* dZ = L.dz + e * L.dz_estride;
-  const int* gidx = L.gather_h ? batch_rows_of(desc, st, e, a.ensemble) : nullptr;
+  const int* gidx = L.gather_h ? batch_rows_of(desc, st, e, a.ensemble, step_off) : nullptr;
   const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
   // the Adam operands are fetched while the gradient tile is being computed
   const int k = tk0 + ty;
@@ -613,19 +657,6 @@ train_update_kernel(UpdArgs a, OptParams opt, const FitDesc* desc, TrainState* s
       if (tn0 + n < L.N && tk0 + kk < L.K) T[(int64_t)(tn0 + n) * L.K + tk0 + kk] = Hs[n][kk];
     }
   }
-  // the last CTA advances optimizer.iterations and fit's step counter
-  __shared__ bool last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    last = (atomicAdd(&st->upd_ticket, 1u) == gridDim.x * gridDim.y - 1);
-  }
-  __syncthreads();
-  if (last && threadIdx.x == 0) {
-    st->iterations += 1;
-    st->fit_step += 1;
-    st->upd_ticket = 0;
-  }
 }
 
 }   // namespace
@@ -653,7 +684,8 @@ struct simba_trainer {
   FitDesc* desc = nullptr;
   std::vector<int> tile_begin;       // update grid: first tile of each layer
   int n_upd_tiles = 0;
-  cudaGraphExec_t fit_graph = nullptr;
+  cudaGraphExec_t fit_graph = nullptr;      // one training step
+  cudaGraphExec_t fit_graph_n = nullptr;    // kGraphSteps consecutive steps (amortises the launch gap)
   cudaStream_t graph_stream = nullptr;
   int launches_per_step = 0;
 };
@@ -722,6 +754,7 @@ static void split_layer(const simba_trainer_t* t, const float* theta_e, int laye
 extern "C" int simba_trainer_destroy(simba_trainer_t* t) {
   if (!t) return SIMBA_OK;
   if (t->fit_graph) cudaGraphExecDestroy(t->fit_graph);
+  if (t->fit_graph_n) cudaGraphExecDestroy(t->fit_graph_n);
   if (t->graph_stream) cudaStreamDestroy(t->graph_stream);
   cudaFree(t->theta); cudaFree(t->thetaT); cudaFree(t->m); cudaFree(t->v); cudaFree(t->grad);
   for (float* p : t->act) cudaFree(p);
@@ -765,7 +798,7 @@ extern "C" int simba_trainer_create(simba_model_t* model, const simba_trainer_co
   }
   t->pn = off;
   t->aligned = (t->U % 4 == 0 && (2 * t->O) % 4 == 0) ? 1 : 0;
-  t->chain_smem = (size_t)(2 * kChunkK * kChunkN + (kChainThreads / 32) * kRows * kChunkN +
+  t->chain_smem = (size_t)(2 * kChunkK * kChunkN + 2 * kSplitK * kHalfRows * kChunkN +
                            2 * kRows * t->ld_act) * sizeof(float);
   if (t->chain_smem > 220 * 1024) {
     const int units = t->U;
@@ -837,7 +870,8 @@ extern "C" int simba_trainer_create(simba_model_t* model, const simba_trainer_co
 // x may be shared by the members (estride 0, validation) or gathered through the fit descriptor.
 static int enqueue_chain(simba_trainer_t* t, const float* x, int64_t x_estride, const float* y,
                          int64_t y_estride, int gather, int grid_rows, int rows_fixed,
-                         const FitDesc* desc, int train, float* out_loss, cudaStream_t s) {
+                         const FitDesc* desc, int train, float* out_loss, int step_off,
+                         cudaStream_t s) {
   const int64_t R = t->cap_rows, B = t->cfg.batch_size;
   ChainArgs a{};
   int np = 0;
@@ -868,19 +902,19 @@ static int enqueue_chain(simba_trainer_t* t, const float* x, int64_t x_estride, 
   a.partial = t->partial; a.tiles_cap = t->tiles_cap; a.train = train; a.out_loss = out_loss;
   dim3 grid((grid_rows + kRows - 1) / kRows, t->E);
   train_chain_kernel<<<grid, kChainThreads, t->chain_smem, s>>>(a, opt_params(t), desc, t->state,
-                                                                rows_fixed);
+                                                                rows_fixed, step_off);
   SIMBA_CUDA_TRY(cudaGetLastError());
   return SIMBA_OK;
 }
 
 static int enqueue_step(simba_trainer_t* t, const float* x, int64_t x_estride, const float* y,
                         int64_t y_estride, int rows_fixed, const FitDesc* desc, float* out_loss,
-                        cudaStream_t s) {
+                        int step_off, cudaStream_t s) {
   const int64_t R = t->cap_rows, B = t->cfg.batch_size;
   const int gather = desc ? 1 : 0;
   const int grid_rows = desc ? t->cfg.batch_size : rows_fixed;
   int rc = enqueue_chain(t, x, x_estride, y, y_estride, gather, grid_rows, rows_fixed, desc, 1,
-                         out_loss, s);
+                         out_loss, step_off, s);
   if (rc) return rc;
   UpdArgs u{};
   for (int l = 0; l <= t->L; ++l) {
@@ -898,7 +932,7 @@ static int enqueue_step(simba_trainer_t* t, const float* x, int64_t x_estride, c
   u.theta = t->theta; u.thetaT = t->thetaT; u.m = t->m; u.v = t->v; u.grad = t->grad;
   u.pn = t->pn; u.pnT = t->pnT; u.ensemble = t->E;
   train_update_kernel<<<dim3(t->n_upd_tiles, t->E), kThreadsU, 0, s>>>(u, opt_params(t), desc,
-                                                                        t->state, rows_fixed);
+                                                                        t->state, rows_fixed, step_off);
   SIMBA_CUDA_TRY(cudaGetLastError());
   return SIMBA_OK;
 }
@@ -908,8 +942,12 @@ extern "C" int simba_trainer_step(simba_trainer_t* t, const float* x, const floa
   if (!t || !x || !y) return set_error(SIMBA_ERR_BAD_CONFIG, "null argument");
   if (rows < 1 || rows > t->cfg.batch_size)
     return set_error(SIMBA_ERR_SHAPE, "rows %d outside [1, batch_size %d]", rows, t->cfg.batch_size);
-  return enqueue_step(t, x, (int64_t)rows * t->IN, y, (int64_t)rows * t->O, rows, nullptr, out_loss,
-                      (cudaStream_t)stream);
+  int rc = enqueue_step(t, x, (int64_t)rows * t->IN, y, (int64_t)rows * t->O, rows, nullptr, out_loss,
+                        0, (cudaStream_t)stream);
+  if (rc) return rc;
+  advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(t->state, 1);
+  SIMBA_CUDA_TRY(cudaGetLastError());
+  return SIMBA_OK;
 }
 
 extern "C" int simba_trainer_fit(simba_trainer_t* t, const float* inputs, const float* targets,
@@ -924,20 +962,28 @@ extern "C" int simba_trainer_fit(simba_trainer_t* t, const float* inputs, const 
   set_fit_desc_kernel<<<1, 1, 0, s>>>(d, t->desc, t->state);
   SIMBA_CUDA_TRY(cudaGetLastError());
   if (!t->fit_graph) {
-    // every pointer the step reads is either owned by the handle or reached through *desc, so one
-    // captured step serves every fit() call
+    // every pointer the step reads is either owned by the handle or reached through *desc, and the
+    // step index lives in device memory, so the captured steps serve every fit() call
     if (!t->graph_stream) SIMBA_CUDA_TRY(cudaStreamCreateWithFlags(&t->graph_stream, cudaStreamNonBlocking));
-    cudaGraph_t graph = nullptr;
-    SIMBA_CUDA_TRY(cudaStreamBeginCapture(t->graph_stream, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_step(t, nullptr, 0, nullptr, 0, B, t->desc, nullptr, t->graph_stream);
-    cudaError_t ce = cudaStreamEndCapture(t->graph_stream, &graph);
-    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    SIMBA_CUDA_TRY(ce);
-    ce = cudaGraphInstantiate(&t->fit_graph, graph, 0);
-    cudaGraphDestroy(graph);
-    SIMBA_CUDA_TRY(ce);
+    for (int which = 0; which < 2; ++which) {
+      cudaGraph_t graph = nullptr;
+      SIMBA_CUDA_TRY(cudaStreamBeginCapture(t->graph_stream, cudaStreamCaptureModeThreadLocal));
+      int rc = SIMBA_OK;
+      const int n = which ? kGraphSteps : 1;
+      for (int i = 0; i < n && rc == SIMBA_OK; ++i)
+        rc = enqueue_step(t, nullptr, 0, nullptr, 0, B, t->desc, nullptr, i, t->graph_stream);
+      advance_kernel<<<1, 1, 0, t->graph_stream>>>(t->state, n);
+      cudaError_t ce = cudaStreamEndCapture(t->graph_stream, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      SIMBA_CUDA_TRY(ce);
+      ce = cudaGraphInstantiate(which ? &t->fit_graph_n : &t->fit_graph, graph, 0);
+      cudaGraphDestroy(graph);
+      SIMBA_CUDA_TRY(ce);
+    }
   }
-  for (int i = 0; i < steps; ++i) SIMBA_CUDA_TRY(cudaGraphLaunch(t->fit_graph, s));
+  int i = 0;
+  for (; i + kGraphSteps <= steps; i += kGraphSteps) SIMBA_CUDA_TRY(cudaGraphLaunch(t->fit_graph_n, s));
+  for (; i < steps; ++i) SIMBA_CUDA_TRY(cudaGraphLaunch(t->fit_graph, s));
   return SIMBA_OK;
 }
 
@@ -948,7 +994,7 @@ extern "C" int simba_trainer_validation(simba_trainer_t* t, const float* x, cons
   cudaStream_t s = (cudaStream_t)stream;
   for (int64_t r0 = 0; r0 < rows; r0 += t->cap_rows) {
     const int nr = (int)((rows - r0) < t->cap_rows ? (rows - r0) : t->cap_rows);
-    int rc = enqueue_chain(t, x + r0 * t->IN, 0, y + r0 * t->O, 0, 0, nr, nr, nullptr, 0, nullptr, s);
+    int rc = enqueue_chain(t, x + r0 * t->IN, 0, y + r0 * t->O, 0, 0, nr, nr, nullptr, 0, nullptr, 0, s);
     if (rc) return rc;
     const int tiles = (nr + kRows - 1) / kRows;
     val_accumulate_kernel<<<1, 32, 0, s>>>(t->partial, t->tiles_cap, tiles, t->E, t->val_acc,

@@ -14,6 +14,6 @@ lib.simba_debug_train_timeline.argtypes = [C.c_void_p]
 assert lib.simba_debug_train_timeline(buf) == 0
 t0 = buf[0]
 print("start->loop %d, loop_end(sum) %d" % (buf[1] - t0, buf[2] - t0))
-for it in range(18):
+for it in range(9):
     b = [buf[8 + it * 8 + j] - t0 for j in range(5)]
     print("chunk %d: top %6d issue %5d wait %5d fma %5d epi %5d" % (it, b[0], b[1] - b[0], b[2] - b[1], b[3] - b[2], b[4] - b[3]))
