@@ -381,7 +381,7 @@ def bench_train(torch, cpu=True, steps=1000, rows=24000):
     torch.cuda.synchronize()
     ms = a.elapsed_time(b)
     ens._trained_ahead = True
-    per_step = int(ens._lib.simba_trainer_launches_per_step(t)) + 1          # + the batch gather
+    per_step = int(ens._lib.simba_trainer_launches_per_step(t))
     out = {"workload": "E=%d x batch %d, 62->4x128->2x60, Adam(clipvalue 1, eps 1e-5); %d steps, data in HBM" % (E, B, steps),
            "steps_per_s": steps / (ms * 1e-3), "us_per_step": ms * 1e3 / steps, "launches_per_step": per_step,
            "loss_first": float(losses[0]), "loss_last": float(losses[steps - 1])}
