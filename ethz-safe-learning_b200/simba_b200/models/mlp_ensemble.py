@@ -171,6 +171,37 @@ class MlpEnsemble(object):
         return (_device.like_input(mu, kind), _device.like_input(torch.sqrt(var), kind),
                 _device.like_input(smp, kind))
 
+    # -- weight hand-off on disk ------------------------------------------
+    def state_arrays(self):
+        """{'member{e}/var{i}': array} in Keras variable order (mlp_ensemble.py:46-50, :28-30):
+        the stable exchange format between a TF/torch-trained ensemble and the planner images."""
+        out = {}
+        for e, member in enumerate(self.ensemble):
+            for i, a in enumerate(member.get_weights()):
+                out['member%d/var%d' % (e, i)] = a
+        return out
+
+    def load_state_arrays(self, arrays):
+        for e, member in enumerate(self.ensemble):
+            n = len(member._arrays)
+            missing = [i for i in range(n) if 'member%d/var%d' % (e, i) not in arrays]
+            if missing:
+                raise KeyError("member %d: variables %s are missing" % (e, missing))
+            member.set_weights([arrays['member%d/var%d' % (e, i)] for i in range(n)])
+
+    def save_weights(self, path):
+        np.savez(path, ensemble_size=self.ensemble_size, n_layers=self.n_layers, units=self.units,
+                 inputs_dim=self.inputs_dim, outputs_dim=self.outputs_dim, **self.state_arrays())
+
+    def load_weights(self, path):
+        with np.load(path) as f:
+            for key, want in (('ensemble_size', self.ensemble_size), ('n_layers', self.n_layers),
+                              ('units', self.units), ('inputs_dim', self.inputs_dim),
+                              ('outputs_dim', self.outputs_dim)):
+                if int(f[key]) != want:
+                    raise ValueError("%s: file has %d, model has %d" % (key, int(f[key]), want))
+            self.load_state_arrays({k: f[k] for k in f.files if k.startswith('member')})
+
     # -- training (mlp_ensemble.py:134-187) --------------------------------------------------------
     EVAL_ROWS = 4096
 

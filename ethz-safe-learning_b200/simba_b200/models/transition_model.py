@@ -115,8 +115,20 @@ class TransitionModel(BaseModel):
                                          _device.stream_ptr()))
         return _device.like_input(out, kind)
 
-    def save(self):
-        pass
+    def save(self, path=None):
+        """The reference's save() is a stub (transition_model.py:89-93). With a path: one .npz with
+        the ensemble's Keras-ordered variables and the scaler statistics."""
+        if path is None:
+            return
+        np.savez(path, inputs_min=self.inputs_min, inputs_max=self.inputs_max,
+                 scale_features=int(bool(self.scale_features)),
+                 ensemble_size=self.model.ensemble_size, n_layers=self.model.n_layers,
+                 units=self.model.units, inputs_dim=self.model.inputs_dim,
+                 outputs_dim=self.model.outputs_dim, **self.model.state_arrays())
 
-    def load(self):
-        pass
+    def load(self, path=None):
+        if path is None:
+            return
+        self.model.load_weights(path)
+        with np.load(path) as f:
+            self.set_statistics(f['inputs_min'], f['inputs_max'])

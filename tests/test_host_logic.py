@@ -113,3 +113,28 @@ def test_fit_has_no_cpu_path_but_statistics_work():
     assert np.all(np.isfinite(tm2.inputs_min)) and np.all(np.isfinite(tm2.inputs_max))
     assert tm2.inputs_min[3] == 0.0 and tm2.inputs_max[3] == 1.0          # lidar bounds kept
     assert tm2.inputs_min[0] == data[:, 0].min()                          # inf replaced by data min
+
+
+def test_weight_handoff_npz_round_trip(tmp_path):
+    """Keras-ordered variables + scaler statistics through one .npz."""
+    from simba_b200.environment_utils import ScorerEnvironment
+    from simba_b200.models import TransitionModel
+    env = ScorerEnvironment()
+    kw = dict(ensemble_size=2, mlp_params=dict(n_layers=2, units=16))
+    a = TransitionModel('mlp_ensemble', env.observation_space, env.action_space, True, True, seed=1, **kw)
+    a._fit_statistics(np.random.default_rng(0).uniform(-3, 3, (50, 62)).astype(np.float32))
+    path = str(tmp_path / 'model.npz')
+    a.save(path)
+    b = TransitionModel('mlp_ensemble', env.observation_space, env.action_space, True, True, seed=2, **kw)
+    assert not np.array_equal(a.model.ensemble[1].get_weights()[0], b.model.ensemble[1].get_weights()[0])
+    b.load(path)
+    for e in range(2):
+        for x, y in zip(a.model.ensemble[e].get_weights(), b.model.ensemble[e].get_weights()):
+            assert np.array_equal(x, y)
+    assert np.array_equal(a.inputs_min, b.inputs_min) and np.array_equal(a.inputs_max, b.inputs_max)
+    c = TransitionModel('mlp_ensemble', env.observation_space, env.action_space, True, True,
+                        ensemble_size=2, mlp_params=dict(n_layers=2, units=8))
+    with pytest.raises(ValueError):
+        c.load(path)
+    a.save()          # the reference's argument-less stubs stay no-ops
+    a.load()
