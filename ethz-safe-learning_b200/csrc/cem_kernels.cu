@@ -2,7 +2,11 @@
 // elite selection (radix select), moment refit, final noise — plus the batch versions of the
 // reference's public scorer / scale / compute_objective methods. All are HBM / latency bound:
 // coalesced, vectorised where the layout allows, no tensor cores.
+#include <cooperative_groups.h>
+
 #include "cem_kernels.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace simba {
 
@@ -335,7 +339,217 @@ __global__ void __launch_bounds__(kSelectThreads) select_elites_kernel(SelectPar
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Large populations (configs[2]: N = 65536, K = 6554): the same selection on a thread-block
+// CLUSTER of 8 CTAs per state. Each CTA keeps its contiguous slice of the order keys in shared
+// memory; per radix pass the 8 slice histograms are combined through distributed shared memory
+// (every CTA reads the other 7 and derives the same digit), so a pass costs one hardware cluster
+// barrier instead of a trip through L2, and the ordered compaction uses the per-CTA (>, ==)
+// counts as its cross-CTA prefix. Output is identical to select_elites_kernel: elites in
+// ascending index order, ties to the lower index, argmax = first max.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSelClusterSize = 8;
+constexpr int kSelClusterMinN = 8192;          // below this one CTA is as fast
+constexpr int kSelClusterMaxSlice = 16384;     // keys per CTA (128 KB of shared memory)
+
+__global__ void __launch_bounds__(kSelectThreads)
+select_elites_cluster_kernel(SelectParams p, int slice) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int s = blockIdx.x / kSelClusterSize;
+  if (p.active != nullptr && p.active[s] == 0) return;      // uniform over the cluster
+  extern __shared__ __align__(16) unsigned long long keys[];   // [slice]
+  __shared__ int hist[2][256];
+  __shared__ int tot[256];
+  __shared__ int warp_sums[32];
+  __shared__ int sh_total;
+  __shared__ int sh_digit, sh_need;
+  __shared__ unsigned long long sh_minmax[2];
+  __shared__ int sh_counts[2];                     // (> T, == T) in this slice
+  __shared__ unsigned long long sh_best_key;
+  __shared__ int sh_best_idx;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int N = p.N, K = p.K;
+  const int lo = min(N, rank * slice), hi = min(N, lo + slice), n_loc = hi - lo;
+  auto load_pair = [&](int i) {
+    const int gsh = i / p.N_local, il = i - gsh * p.N_local;
+    return reinterpret_cast<const float2*>(p.pairs_all)[((long)gsh * p.S + s) * p.N_local + il];
+  };
+
+  // ---- stage this slice's order keys in shared memory, find the global key range ---------------
+  if (tid == 0) { sh_best_key = 0ull; sh_best_idx = 0x7fffffff; sh_minmax[0] = ~0ull; sh_minmax[1] = 0ull; }
+  __syncthreads();
+  {
+    unsigned long long kmin = ~0ull, kmax = 0ull;
+    for (int base = 0; base < n_loc; base += 4 * kSelectThreads) {
+      float2 pr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = base + u * kSelectThreads + tid;
+        pr[u] = j < n_loc ? load_pair(lo + j) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = base + u * kSelectThreads + tid;
+        if (j < n_loc) {
+          const unsigned long long k = pair_key(p.objective, pr[u].x, pr[u].y, p.c_max);
+          keys[j] = k;
+          kmin = k < kmin ? k : kmin;
+          kmax = k > kmax ? k : kmax;
+          if (p.out_scores != nullptr)
+            p.out_scores[(long)s * N + lo + j] = pair_score(p.objective, pr[u].x, pr[u].y, p.c_max);
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long a = __shfl_xor_sync(0xffffffffu, kmin, d), c = __shfl_xor_sync(0xffffffffu, kmax, d);
+      kmin = a < kmin ? a : kmin;
+      kmax = c > kmax ? c : kmax;
+    }
+    if (lane == 0) { atomicMin(&sh_minmax[0], kmin); atomicMax(&sh_minmax[1], kmax); }
+  }
+  cluster.sync();
+  unsigned long long kmin = ~0ull, kmax = 0ull;
+  for (int r = 0; r < kSelClusterSize; ++r) {
+    const unsigned long long* mm = cluster.map_shared_rank(sh_minmax, r);
+    kmin = mm[0] < kmin ? mm[0] : kmin;
+    kmax = mm[1] > kmax ? mm[1] : kmax;
+  }
+  const unsigned long long span = kmax - kmin;
+
+  // ---- MSD radix select of the K-th largest key on (key - kmin) ---------------------------------
+  uint64_t prefix = 0ull, mask = 0ull;
+  int need = K;
+  int top_byte = 7;
+  while (top_byte > 0 && ((span >> (8 * top_byte)) & 0xffull) == 0ull) --top_byte;
+  int buf = 0;
+  for (int byte = top_byte; byte >= 0; --byte, buf ^= 1) {
+    if (tid < 256) hist[buf][tid] = 0;
+    __syncthreads();
+    const int shift = 8 * byte;
+    for (int base = 0; base < n_loc; base += kSelectThreads) {
+      const int j = base + tid;
+      int bin = -1;
+      if (j < n_loc) {
+        const uint64_t k = keys[j] - kmin;
+        if ((k & mask) == prefix) bin = (int)((k >> shift) & 0xffull);
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, bin);
+      if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[buf][bin], __popc(peers));
+    }
+    cluster.sync();                            // every slice's histogram of this pass is complete
+    if (tid < 256) {
+      int t = 0;
+      for (int r = 0; r < kSelClusterSize; ++r) t += cluster.map_shared_rank(&hist[buf][0], r)[tid];
+      tot[tid] = t;
+    }
+    __syncthreads();
+    if (tid < 256) {
+      int above = 0;
+      for (int bb = tid + 1; bb < 256; ++bb) above += tot[bb];
+      if (above < need && need <= above + tot[tid]) { sh_digit = tid; sh_need = need - above; }
+    }
+    __syncthreads();
+    prefix |= (uint64_t)sh_digit << shift;
+    mask |= 0xffull << shift;
+    need = sh_need;
+    __syncthreads();
+    // hist[buf] may still be read by the other CTAs; it is only zeroed again two passes later,
+    // after the next pass's cluster barrier
+  }
+  const uint64_t T = prefix + kmin;   // K-th largest key; `need` of the keys == T are taken, lowest index first
+
+  // ---- ordered compaction: thread = contiguous range of the slice, CTA = contiguous slice -----
+  const int V = (n_loc + kSelectThreads - 1) / kSelectThreads;
+  const int tlo = min(n_loc, tid * V), thi = min(n_loc, tlo + V);
+  int eq_local = 0, gt_local = 0;
+  uint64_t best_k = 0ull;
+  int best_i = 0x7fffffff;
+  for (int j = tlo; j < thi; ++j) {
+    const uint64_t k = keys[j];
+    eq_local += (k == T);
+    gt_local += (k > T);
+    if (k > best_k || best_i == 0x7fffffff) { best_k = k; best_i = lo + j; }   // first max in range
+  }
+  const int eq_before_cta = block_exclusive_scan<kSelectThreads>(eq_local, warp_sums, &sh_total);
+  const int eq_cta = sh_total;
+  __syncthreads();
+  (void)block_exclusive_scan<kSelectThreads>(gt_local, warp_sums, &sh_total);
+  if (tid == 0) { sh_counts[0] = sh_total; sh_counts[1] = eq_cta; }
+  if (best_i != 0x7fffffff) atomicMax(&sh_best_key, (unsigned long long)best_k);
+  __syncthreads();
+  if (best_i != 0x7fffffff && best_k == sh_best_key) atomicMin(&sh_best_idx, best_i);
+  cluster.sync();                              // counts and per-slice best of every CTA are visible
+  int eq_before = 0, pos_base = 0;
+  unsigned long long gbest_key = 0ull;
+  int gbest_idx = 0x7fffffff;
+  for (int r = 0; r < kSelClusterSize; ++r) {
+    const int* cnt = cluster.map_shared_rank(sh_counts, r);
+    const int gt_r = cnt[0], eq_r = cnt[1];
+    if (r < rank) {
+      pos_base += gt_r + max(0, min(eq_r, need - eq_before));
+      eq_before += eq_r;
+    }
+    const unsigned long long bk = *cluster.map_shared_rank(&sh_best_key, r);
+    const int bi = *cluster.map_shared_rank(&sh_best_idx, r);
+    if (bi != 0x7fffffff && (gbest_idx == 0x7fffffff || bk > gbest_key)) { gbest_key = bk; gbest_idx = bi; }
+  }
+  const int eq_seen = eq_before + eq_before_cta;                         // == T keys at lower indices
+  const int eq_take = max(0, min(eq_local, need - eq_seen));
+  int pos = pos_base + block_exclusive_scan<kSelectThreads>(gt_local + eq_take, warp_sums, &sh_total);
+  int eq_run = eq_seen;
+  for (int j = tlo; j < thi; ++j) {
+    const uint64_t k = keys[j];
+    bool sel = k > T;
+    if (k == T) { sel = eq_run < need; ++eq_run; }
+    if (sel) p.out_elite[(long)s * K + pos++] = lo + j;
+  }
+
+  // ---- best of elite = global best key, lowest index among ties (slices are index-ordered, so
+  //      the first slice holding the maximum wins) ------------------------------------------------
+  if (rank == 0) {
+    const float2 pr = load_pair(gbest_idx);
+    const float top_score = pair_score(p.objective, pr.x, pr.y, p.c_max);
+    if (top_score > p.best_score[s]) {                       // cem_mpc.py:58 strict '>'
+      if (tid < p.A) p.best_action[s * p.A + tid] = p.actions[((long)s * N + gbest_idx) * p.H * p.A + tid];
+      __syncthreads();
+      if (tid == 0) p.best_score[s] = top_score;
+    }
+  }
+  cluster.sync();                              // no CTA may exit while its shared memory is being read
+}
+
+static bool use_cluster_path(int N) {
+  return N >= kSelClusterMinN && (N + kSelClusterSize - 1) / kSelClusterSize <= kSelClusterMaxSlice;
+}
+
+template <typename Kernel, typename... Args>
+static cudaError_t launch_cluster(Kernel kernel, int n_states, int threads, size_t smem, cudaStream_t st,
+                                  Args... args) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_states * kSelClusterSize);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kSelClusterSize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 cudaError_t launch_select_elites(const SelectParams& p, cudaStream_t st) {
+  if (use_cluster_path(p.N)) {
+    const int slice = (p.N + kSelClusterSize - 1) / kSelClusterSize;
+    return launch_cluster(select_elites_cluster_kernel, p.S, kSelectThreads,
+                          (size_t)slice * sizeof(unsigned long long), st, p, slice);
+  }
   select_elites_kernel<<<p.S, kSelectThreads, 0, st>>>(p);
   return cudaGetLastError();
 }
@@ -420,9 +634,98 @@ __global__ void __launch_bounds__(kRefitThreads) refit_kernel(RefitParams p) {
   refit_body(p, s, p.elite + (long)s * p.K, sh);
 }
 
+// Large elite sets: the K gathers are spread over a cluster of 8 CTAs per state; the per-CTA
+// column sums are combined in rank order through distributed shared memory (every CTA derives the
+// same mean / variance), two cluster barriers per refit.
+__global__ void __launch_bounds__(kRefitThreads) refit_cluster_kernel(RefitParams p) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int s = blockIdx.x / kSelClusterSize;
+  if (p.active != nullptr && p.active[s] == 0) return;      // uniform over the cluster
+  extern __shared__ float sh[];           // [groups][HA] partials, [HA] CTA sums, [HA] mean, [HA] sigma
+  const int HA = p.H * p.A;
+  const int groups = kRefitThreads / HA > 0 ? kRefitThreads / HA : 1;
+  float* part = sh;
+  float* cta_sum = part + groups * HA;
+  float* mean = cta_sum + HA;
+  float* sig = mean + HA;
+  const int tid = threadIdx.x;
+  const float* acts = p.actions + (long)s * p.N * HA;
+  const int* elite = p.elite + (long)s * p.K;
+  const float kf = (float)p.K;
+  const int per = (p.K + kSelClusterSize - 1) / kSelClusterSize;
+  const int k_lo = min(p.K, rank * per), k_hi = min(p.K, k_lo + per);
+  const int c = tid % HA, grp = tid / HA;
+
+  for (int pass = 0; pass < 2; ++pass) {
+    if (grp < groups) {
+      float acc = 0.0f;
+      const float m = pass ? mean[c] : 0.0f;
+      int k = k_lo + grp;
+      for (; k + 7 * groups < k_hi; k += 8 * groups) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = acts[(long)elite[k + u * groups] * HA + c];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (pass) { const float d = __fsub_rn(v[u], m); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
+          else acc = __fadd_rn(acc, v[u]);
+        }
+      }
+      for (; k < k_hi; k += groups) {
+        const float v = acts[(long)elite[k] * HA + c];
+        if (pass) { const float d = __fsub_rn(v, m); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
+        else acc = __fadd_rn(acc, v);
+      }
+      part[grp * HA + c] = acc;
+    }
+    __syncthreads();
+    for (int cc = tid; cc < HA; cc += kRefitThreads) {
+      float t = 0.0f;
+      for (int gI = 0; gI < groups; ++gI) t = __fadd_rn(t, part[gI * HA + cc]);
+      cta_sum[cc] = t;
+    }
+    cluster.sync();                            // every CTA's column sums of this pass are visible
+    for (int cc = tid; cc < HA; cc += kRefitThreads) {
+      float t = 0.0f;
+      for (int r = 0; r < kSelClusterSize; ++r) t = __fadd_rn(t, cluster.map_shared_rank(cta_sum, r)[cc]);
+      const float r_ = __fdiv_rn(t, kf);
+      if (pass == 0) mean[cc] = r_;
+      else {
+        const float sd = sqrtf(r_);                                       // cem_mpc.py:63
+        const float mu_new = __fadd_rn(__fmul_rn(p.smoothing, p.mu[s * HA + cc]),
+                                       __fmul_rn(p.one_minus_smoothing, mean[cc]));
+        const float sg_new = __fadd_rn(__fmul_rn(p.smoothing, p.sigma[s * HA + cc]),
+                                       __fmul_rn(p.one_minus_smoothing, sd));
+        sig[cc] = sg_new;
+        mean[cc] = mu_new;
+      }
+    }
+    cluster.sync();                            // remote reads of cta_sum are done before it is rewritten
+  }
+  if (rank == 0) {
+    // mu / sigma are read by every CTA above and written only here, after the last barrier
+    for (int cc = tid; cc < HA; cc += kRefitThreads) {
+      p.mu[s * HA + cc] = mean[cc];                                       // cem_mpc.py:64-65
+      p.sigma[s * HA + cc] = sig[cc];
+    }
+    if (tid == 0) {
+      float t = 0.0f;
+      for (int cc = 0; cc < HA; ++cc) t = __fadd_rn(t, sig[cc]);
+      if (p.iterations_run != nullptr) p.iterations_run[s] += 1;
+      if (p.active != nullptr && __fdiv_rn(t, (float)HA) <= p.stddev_threshold)  // cem_mpc.py:66-67
+        p.active[s] = 0;
+    }
+  }
+}
+
 cudaError_t launch_refit(const RefitParams& p, cudaStream_t st) {
   const int HA = p.H * p.A;
   const int groups = kRefitThreads / HA > 0 ? kRefitThreads / HA : 1;
+  if (p.K >= 2048) {
+    const size_t smem = (size_t)(groups * HA + 3 * HA) * sizeof(float);
+    return launch_cluster(refit_cluster_kernel, p.S, kRefitThreads, smem, st, p);
+  }
   const size_t smem = (size_t)(groups * HA + 2 * HA) * sizeof(float);
   refit_kernel<<<p.S, kRefitThreads, smem, st>>>(p);
   return cudaGetLastError();

@@ -325,3 +325,49 @@ def test_select_large_population_with_ties(lib):
     order = np.argsort(-scores, kind='stable')
     assert np.array_equal(elite.cpu().numpy(), np.sort(order[:c['K']]))
     assert float(best_s.cpu()[0]) == scores[order[0]]
+
+
+@pytest.mark.parametrize("N,K,S,levels", [(10007, 2500, 2, 40), (8192, 8192, 1, 5), (9000, 1, 1, 0),
+                                          (65536, 6554, 1, 0), (20000, 2047, 3, 3)])
+def test_cluster_select_and_refit_match_numpy(lib, N, K, S, levels):
+    """The thread-block-cluster kernels used for large populations (N >= 8192: select on 8 CTAs
+    per state with DSMEM histograms; K >= 2048: refit on 8 CTAs): uneven slices, several states,
+    heavy ties (levels > 0 quantises the returns), K == N and K == 1. Elite indices, best action
+    and scores exact; moments within 1e-5 (summation order differs from numpy's)."""
+    from simba_b200 import _lib
+    c = helpers.workload('tiny', N=N, K=K, P=8, E=2, S=S)
+    pol = helpers.cuda_policy(c, 'penalty', n_states=S)
+    pl = pol._ensure_planner()
+    H, A = c['H'], c['A']
+    rng = np.random.default_rng(N + K)
+    ret = rng.normal(0, 1, (S, N)).astype(np.float32)
+    if levels:
+        ret = (np.round(ret * levels) / levels).astype(np.float32)
+    cost = rng.integers(0, 3, (S, N)).astype(np.float32)
+    pairs = dev(np.stack([ret, cost], -1))
+    acts = rng.uniform(-1, 1, (S, N, H, A)).astype(np.float32)
+    d_acts = dev(acts)
+    elite = torch.empty((S, K), dtype=torch.int32, device='cuda')
+    sc_out = torch.empty((S, N), dtype=torch.float32, device='cuda')
+    best_a = torch.zeros((S, A), dtype=torch.float32, device='cuda')
+    best_s = torch.full((S,), -np.inf, dtype=torch.float32, device='cuda')
+    _lib.check(lib.simba_select_elites(pl, P(pairs), P(d_acts), None, P(elite), P(sc_out), P(best_a),
+                                       P(best_s), None))
+    c_max = so.beta_count_threshold(8, 0.15)
+    scores = ret - (cost > c_max).astype(np.float32) * np.float32(100)
+    assert np.array_equal(sc_out.cpu().numpy(), scores)
+    want = []
+    for s in range(S):
+        order = np.argsort(-scores[s], kind='stable')
+        want.append(np.sort(order[:K]))
+        assert np.array_equal(elite.cpu().numpy()[s], want[s]), s
+        assert float(best_s.cpu()[s]) == scores[s, order[0]]
+        assert np.array_equal(best_a.cpu().numpy()[s], acts[s, order[0], 0])
+    mu = dev(np.zeros((S, H, A), np.float32)); sg = dev(np.ones((S, H, A), np.float32))
+    active = dev(np.ones(S, np.int32)); iters = dev(np.zeros(S, np.int32))
+    _lib.check(lib.simba_refit(pl, P(d_acts), P(elite), P(mu), P(sg), P(active), P(iters), None))
+    for s in range(S):
+        m0, v0 = so.tf_moments_axis0(acts[s][want[s]].astype(np.float64))
+        assert np.allclose(mu.cpu().numpy()[s], m0, rtol=1e-5, atol=1e-6)
+        assert np.allclose(sg.cpu().numpy()[s], np.sqrt(v0), rtol=1e-5, atol=1e-6)
+    assert np.array_equal(iters.cpu().numpy(), np.ones(S, np.int32))
