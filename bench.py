@@ -56,7 +56,32 @@ class ClockSampler(object):
     def __init__(self, index):
         self.index, self.rows, self.stop_flag, self.th = index, [], False, None
 
+    def _run_nvml(self):
+        """In-process NVML polling (5 ms period) so that even a sub-second timed region is sampled
+        many times; same fields as the nvidia-smi query."""
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        bits = [("hw_slowdown", getattr(pynvml, 'nvmlClocksThrottleReasonHwSlowdown', 0x8)),
+                ("hw_thermal_slowdown", getattr(pynvml, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40)),
+                ("sw_thermal_slowdown", getattr(pynvml, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20)),
+                ("sw_power_cap", getattr(pynvml, 'nvmlClocksThrottleReasonSwPowerCap', 0x4))]
+        while not self.stop_flag:
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            try:
+                mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            except Exception:
+                mask = 0
+            self.rows.append([str(sm), str(mx)] + ['Active' if mask & b else 'Not Active' for _, b in bits])
+            time.sleep(0.005)
+
     def _run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass
         while not self.stop_flag:
             try:
                 out = subprocess.check_output(

@@ -35,7 +35,8 @@ def _data(rng, members, rows, n_in, n_out, scale=1.0):
     return x, y
 
 
-@pytest.mark.parametrize('shape', [(62, 60, 5, 64, 4, 128), (12, 10, 3, 16, 2, 40), (7, 5, 2, 9, 1, 33)])
+@pytest.mark.parametrize('shape', [(62, 60, 5, 64, 4, 128), (12, 10, 3, 16, 2, 40), (7, 5, 2, 9, 1, 33),
+                                   (62, 60, 2, 32, 2, 400), (20, 18, 2, 24, 3, 200), (9, 7, 1, 5, 2, 130)])
 def test_one_step_matches_oracle(shape):
     n_in, n_out, E, B, L, U = shape
     ens = _ensemble(n_in, n_out, E, B, L, U)
