@@ -163,3 +163,40 @@ def test_training_twice_gives_identical_results():
         out.append(ens.trainer_arrays('weights', 1))
     for a, b in zip(*out):
         np.testing.assert_array_equal(a, b)
+
+
+from hypothesis import HealthCheck, assume, given, settings  # noqa: E402
+from hypothesis import strategies as st                      # noqa: E402
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+@given(n_out=st.integers(1, 70), n_act=st.integers(1, 6), E=st.integers(1, 6), B=st.integers(1, 70),
+       rows_frac=st.floats(0.0, 1.0), L=st.integers(1, 5), U=st.integers(1, 300),
+       steps=st.integers(1, 3), seed=st.integers(0, 2 ** 31 - 1))
+def test_training_step_random_shapes(n_out, n_act, E, B, rows_frac, L, U, steps, seed):
+    """Random layer widths (aligned and unaligned, one and several weight chunks), batch sizes that
+    do not fill a row tile, fewer rows than batch_size: loss and weights follow the oracle."""
+    n_in = n_out + n_act
+    rows = max(1, int(round(rows_frac * B)))
+    ens = _ensemble(n_in, n_out, E, B, L, U, lr=1e-3, seed=seed % 1000)
+    ora = _oracle(ens)
+    rng = np.random.default_rng(seed)
+    for _ in range(steps):
+        x, y = _data(rng, E, rows, n_in, n_out)
+        # a hidden pre-activation within rounding distance of the ReLU kink may be masked differently
+        # by two correct fp32 implementations (and then a whole unit's gradient differs): skip those
+        for e, net in enumerate(ora.nets):
+            h = x[e]
+            for l in range(L):
+                z = h @ net.arrays[2 * l] + net.arrays[2 * l + 1]
+                assume(np.abs(z).min() > 1e-5)
+                h = np.maximum(z, 0)
+        got, want = float(ens.training_step(x, y)), float(ora.training_step(x, y))
+        assert got == pytest.approx(want, rel=2e-4, abs=1e-6)
+    n_var = 2 * L + 4
+    for e in range(E):
+        for g, r in zip(ens.trainer_arrays('grads', e), ora.last_grads[e * n_var:(e + 1) * n_var]):
+            np.testing.assert_allclose(g, r, rtol=2e-3, atol=2e-6)
+        for g, r in zip(ens.trainer_arrays('weights', e), ora.nets[e].arrays):
+            np.testing.assert_allclose(g, r, rtol=0, atol=4e-3 * steps)
+    assert ens.iterations == steps
