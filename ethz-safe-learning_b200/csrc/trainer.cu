@@ -36,13 +36,13 @@ using namespace simba;
 
 namespace {
 
-constexpr int kRows = 8;         // batch rows per chain CTA (64-row batch x 5 members -> 40 CTAs)
+// batch rows per chain CTA: template parameter R of the chain kernel (4, 8 or 16; the host picks
+// the smallest that keeps the grid near one wave: 64-row batch x 5 members -> R = 4, 80 CTAs)
 constexpr int kChunkK = 128;     // weight chunk: [128 k] x [128 n] fp32 = 64 KB, two in flight
 constexpr int kChunkN = 128;
 constexpr int kChainThreads = 256;
-constexpr int kSplitK = 4;       // warps 0-3: first half of the rows, warps 4-7: second half; 4-way split-K
-constexpr int kHalfRows = kRows / 2;
-constexpr int kEpiRows = kRows / 8;   // epilogue rows per warp
+constexpr int kChainWarps = 8;
+__host__ __device__ constexpr int chain_row_groups(int rows) { return rows > 8 ? 2 : 1; }   // 16 rows: 2 row groups x 4 k-slices
 constexpr int kTileU = 32;       // update kernel: [32 k] x [32 n] tile of dtheta
 constexpr int kRowsU = 64;       // update kernel: batch rows per staged chunk
 constexpr int kThreadsU = 256;
@@ -261,18 +261,25 @@ __device__ __forceinline__ void issue_chunk(const ChainArgs& a, const ChunkCurso
   }
 }
 
-// The multiply: warps 0-3 own the first half of the tile's rows and warps 4-7 the second; within
-// a half the four warps split K (warp s takes k-groups s, s + 4, ...). A lane owns 4 columns, so
-// a thread accumulates a [kHalfRows x 4] register tile of independent FMA chains, and the
-// operands of a k-group (4 weight float4s + kHalfRows broadcast activation float4s) sit in
-// registers ahead of their use. The four partial tiles of a half are added in a fixed order
+// The multiply: the 8 warps form kRowGroups row groups x kSplitK k-slices (R <= 8: 1 x 8, i.e.
+// every warp covers all rows of the tile and one eighth of K, so each weight element is read
+// from shared memory exactly once per CTA; R = 16: 2 x 4 to bound the register tile). Warp slice s takes k-groups s, s + kSplitK, ... A
+// lane owns 4 columns, so a thread accumulates a [kGroupRows x 4] register tile of independent
+// FMA chains, and the operands of a k-group (4 weight float4s + kGroupRows broadcast activation
+// float4s) sit in registers ahead of their use. The partial tiles are added in a fixed order
 // through shared memory when the layer's last chunk is done.
+template <int kRows>
 __global__ void __launch_bounds__(kChainThreads)
 train_chain_kernel(ChainArgs a, OptParams opt, const FitDesc* desc, TrainState* st, int rows_fixed,
                    int step_off) {
+  constexpr int kRowGroups = chain_row_groups(kRows);   // the 8 warps: kRowGroups row groups x kSplitK k-slices
+  constexpr int kSplitK = kChainWarps / kRowGroups;
+  constexpr int kGroupRows = kRows / kRowGroups;
+  constexpr int kEpiWarps = kRows < kChainWarps ? kRows : kChainWarps;   // warps that own rows in the epilogue
+  constexpr int kEpiRows = kRows / kEpiWarps;                            // rows per such warp
   extern __shared__ __align__(16) float smem[];
   float* red = smem + 2 * kChunkK * kChunkN;                 // [2 halves][4 k-slices][8][128]
-  float* act0 = red + 2 * kSplitK * kHalfRows * kChunkN;
+  float* act0 = red + kRowGroups * kSplitK * kGroupRows * kChunkN;
   float* act1 = act0 + kRows * a.ld_act;
   __shared__ float scratch[kChainThreads / 32];
   __shared__ __align__(8) unsigned long long bars[2];
@@ -281,7 +288,7 @@ train_chain_kernel(ChainArgs a, OptParams opt, const FitDesc* desc, TrainState* 
   const int rows = resolve_rows(desc, st, rows_fixed, step_off);
   const int e = blockIdx.y, r0 = blockIdx.x * kRows;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int half = warp >> 2, kslice = warp & 3;    // multiply: rows 8 half .. 8 half + 7
+  const int rgroup = warp / kSplitK, kslice = warp % kSplitK;   // multiply: rows kGroupRows * rgroup ..
   const int cl = 4 * lane;                          // chunk-local columns cl .. cl + 3 (both phases)
   // epilogue: warp w finishes rows kEpiRows * w .. of the tile
   const int ld = a.ld_act;
@@ -316,7 +323,7 @@ train_chain_kernel(ChainArgs a, OptParams opt, const FitDesc* desc, TrainState* 
     __syncthreads();
     float* in = act0;
     float* out = act1;
-    float acc[kHalfRows][4] = {};
+    float acc[kGroupRows][4] = {};
     int q = 0;
     TL(1);
     while (true) {
@@ -343,7 +350,7 @@ train_chain_kernel(ChainArgs a, OptParams opt, const FitDesc* desc, TrainState* 
 #pragma unroll
         for (int i = 0; i < kEpiRows; ++i) {
           const int r = r0 + kEpiRows * warp + i;
-          if (r >= rows) continue;
+          if (warp >= kEpiWarps || r >= rows) continue;
           if (p.kind == kPassBackward) {
             const float* h = p.mask + e * p.mask_estride + (int64_t)r * p.n_dim;
 #pragma unroll
@@ -364,32 +371,32 @@ train_chain_kernel(ChainArgs a, OptParams opt, const FitDesc* desc, TrainState* 
       {
         const int S = chunk_stride(a, p);
         const float* w = wb + cl;
-        const float* xin = in + (half * kHalfRows) * ld + cur.k0;
+        const float* xin = in + (rgroup * kGroupRows) * ld + cur.k0;
         for (int kk = 4 * kslice; kk < kc4; kk += 4 * kSplitK) {
           const float4 w0 = *reinterpret_cast<const float4*>(w + (kk + 0) * S);
           const float4 w1 = *reinterpret_cast<const float4*>(w + (kk + 1) * S);
           const float4 w2 = *reinterpret_cast<const float4*>(w + (kk + 2) * S);
           const float4 w3 = *reinterpret_cast<const float4*>(w + (kk + 3) * S);
-          float4 x[kHalfRows];
+          float4 x[kGroupRows];
 #pragma unroll
-          for (int i = 0; i < kHalfRows; ++i) x[i] = *reinterpret_cast<const float4*>(xin + i * ld + kk);
+          for (int i = 0; i < kGroupRows; ++i) x[i] = *reinterpret_cast<const float4*>(xin + i * ld + kk);
 #pragma unroll
-          for (int i = 0; i < kHalfRows; ++i) {
+          for (int i = 0; i < kGroupRows; ++i) {
             acc[i][0] = fmaf(x[i].x, w0.x, acc[i][0]); acc[i][1] = fmaf(x[i].x, w0.y, acc[i][1]);
             acc[i][2] = fmaf(x[i].x, w0.z, acc[i][2]); acc[i][3] = fmaf(x[i].x, w0.w, acc[i][3]);
           }
 #pragma unroll
-          for (int i = 0; i < kHalfRows; ++i) {
+          for (int i = 0; i < kGroupRows; ++i) {
             acc[i][0] = fmaf(x[i].y, w1.x, acc[i][0]); acc[i][1] = fmaf(x[i].y, w1.y, acc[i][1]);
             acc[i][2] = fmaf(x[i].y, w1.z, acc[i][2]); acc[i][3] = fmaf(x[i].y, w1.w, acc[i][3]);
           }
 #pragma unroll
-          for (int i = 0; i < kHalfRows; ++i) {
+          for (int i = 0; i < kGroupRows; ++i) {
             acc[i][0] = fmaf(x[i].z, w2.x, acc[i][0]); acc[i][1] = fmaf(x[i].z, w2.y, acc[i][1]);
             acc[i][2] = fmaf(x[i].z, w2.z, acc[i][2]); acc[i][3] = fmaf(x[i].z, w2.w, acc[i][3]);
           }
 #pragma unroll
-          for (int i = 0; i < kHalfRows; ++i) {
+          for (int i = 0; i < kGroupRows; ++i) {
             acc[i][0] = fmaf(x[i].w, w3.x, acc[i][0]); acc[i][1] = fmaf(x[i].w, w3.y, acc[i][1]);
             acc[i][2] = fmaf(x[i].w, w3.z, acc[i][2]); acc[i][3] = fmaf(x[i].w, w3.w, acc[i][3]);
           }
@@ -397,24 +404,25 @@ train_chain_kernel(ChainArgs a, OptParams opt, const FitDesc* desc, TrainState* 
       }
       TL(8 + q * 8 + 3);
       if (last_k) {
-        // add the four k-slices of each half in slice order, then the epilogue of this warp's rows,
+        // add the k-slices of each row group in slice order, then the epilogue of this warp's rows,
         // columns c0 .. c0 + 3
 #pragma unroll
-        for (int i = 0; i < kHalfRows; ++i) {
-          *reinterpret_cast<float4*>(red + ((half * kSplitK + kslice) * kHalfRows + i) * kChunkN + cl) =
+        for (int i = 0; i < kGroupRows; ++i) {
+          *reinterpret_cast<float4*>(red + ((rgroup * kSplitK + kslice) * kGroupRows + i) * kChunkN + cl) =
               make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
           acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
         }
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < kEpiRows; ++i) {
+          if (warp >= kEpiWarps) continue;
           const int rl = kEpiRows * warp + i, r = r0 + rl;
           const bool row_ok = r < rows;
           float v[4] = {};
 #pragma unroll
           for (int sl = 0; sl < kSplitK; ++sl) {
             const float4 pv = *reinterpret_cast<const float4*>(
-                red + (((rl / kHalfRows) * kSplitK + sl) * kHalfRows + (rl % kHalfRows)) * kChunkN + cl);
+                red + (((rl / kGroupRows) * kSplitK + sl) * kGroupRows + (rl % kGroupRows)) * kChunkN + cl);
             v[0] += pv.x; v[1] += pv.y; v[2] += pv.z; v[3] += pv.w;
           }
           if (p.kind == kPassHead) {
@@ -661,6 +669,13 @@ train_update_kernel(UpdArgs a, OptParams opt, const FitDesc* desc, const TrainSt
 
 }   // namespace
 
+static size_t chain_smem_bytes(int tile_rows, int ld_act) {
+  // weight ring + partial tiles [8 warps worth of (rows / groups) x 128] + two activation tiles
+  return (size_t)(2 * kChunkK * kChunkN + kChainWarps * (tile_rows / chain_row_groups(tile_rows)) * kChunkN +
+                  2 * tile_rows * ld_act) * sizeof(float);
+}
+
+
 // ---------------------------------------------------------------------------------------------
 // handle
 // ---------------------------------------------------------------------------------------------
@@ -689,6 +704,12 @@ struct simba_trainer {
   cudaStream_t graph_stream = nullptr;
   int launches_per_step = 0;
 };
+
+static int chain_tile_rows(const simba_trainer_t* t, int grid_rows) {
+  for (int R : {4, 8})
+    if ((int64_t)t->E * ((grid_rows + R - 1) / R) <= 160) return R;
+  return 16;
+}
 
 static OptParams opt_params(const simba_trainer_t* t) {
   OptParams o;
@@ -798,8 +819,8 @@ extern "C" int simba_trainer_create(simba_model_t* model, const simba_trainer_co
   }
   t->pn = off;
   t->aligned = (t->U % 4 == 0 && (2 * t->O) % 4 == 0) ? 1 : 0;
-  t->chain_smem = (size_t)(2 * kChunkK * kChunkN + 2 * kSplitK * kHalfRows * kChunkN +
-                           2 * kRows * t->ld_act) * sizeof(float);
+  // largest variant (16-row tiles): weight ring + partial tiles + two activation tiles
+  t->chain_smem = chain_smem_bytes(16, t->ld_act);
   if (t->chain_smem > 220 * 1024) {
     const int units = t->U;
     delete t;
@@ -837,8 +858,12 @@ extern "C" int simba_trainer_create(simba_model_t* model, const simba_trainer_co
     TRY_OR_FREE(cudaMalloc(&t->thetaT, hostT.size() * sizeof(float)));
     TRY_OR_FREE(cudaMemcpy(t->thetaT, hostT.data(), hostT.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
-  TRY_OR_FREE(cudaFuncSetAttribute(train_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)t->chain_smem));
+  TRY_OR_FREE(cudaFuncSetAttribute(train_chain_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)chain_smem_bytes(4, t->ld_act)));
+  TRY_OR_FREE(cudaFuncSetAttribute(train_chain_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)chain_smem_bytes(8, t->ld_act)));
+  TRY_OR_FREE(cudaFuncSetAttribute(train_chain_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)chain_smem_bytes(16, t->ld_act)));
   TRY_OR_FREE(cudaMemset(t->m, 0, pbytes));
   TRY_OR_FREE(cudaMemset(t->v, 0, pbytes));
   TRY_OR_FREE(cudaMemset(t->grad, 0, pbytes));
@@ -849,7 +874,7 @@ extern "C" int simba_trainer_create(simba_model_t* model, const simba_trainer_co
     TRY_OR_FREE(cudaMalloc(&t->act[l], (size_t)E * R * t->K[l] * sizeof(float)));
     TRY_OR_FREE(cudaMalloc(&t->dz[l], (size_t)E * cfg->batch_size * t->N[l] * sizeof(float)));
   }
-  t->tiles_cap = (int)((R + kRows - 1) / kRows);
+  t->tiles_cap = (int)((R + 3) / 4);                    // smallest row tile
   TRY_OR_FREE(cudaMalloc(&t->partial, (size_t)E * t->tiles_cap * 2 * sizeof(float)));
   TRY_OR_FREE(cudaMalloc(&t->val_acc, (size_t)E * 2 * sizeof(double)));
   TRY_OR_FREE(cudaMalloc(&t->state, sizeof(TrainState)));
@@ -900,9 +925,17 @@ static int enqueue_chain(simba_trainer_t* t, const float* x, int64_t x_estride, 
   a.theta = t->theta; a.thetaT = t->thetaT; a.pn = t->pn; a.pnT = t->pnT;
   a.ld_act = t->ld_act; a.out_dim = t->O; a.ensemble = t->E; a.aligned = t->aligned;
   a.partial = t->partial; a.tiles_cap = t->tiles_cap; a.train = train; a.out_loss = out_loss;
-  dim3 grid((grid_rows + kRows - 1) / kRows, t->E);
-  train_chain_kernel<<<grid, kChainThreads, t->chain_smem, s>>>(a, opt_params(t), desc, t->state,
-                                                                rows_fixed, step_off);
+  // the smallest row tile that keeps the grid within about one wave of SMs
+  const int TR = chain_tile_rows(t, grid_rows);
+  dim3 grid((grid_rows + TR - 1) / TR, t->E);
+  const size_t smem = chain_smem_bytes(TR, t->ld_act);
+  const OptParams opt = opt_params(t);
+  if (TR == 4)
+    train_chain_kernel<4><<<grid, kChainThreads, smem, s>>>(a, opt, desc, t->state, rows_fixed, step_off);
+  else if (TR == 8)
+    train_chain_kernel<8><<<grid, kChainThreads, smem, s>>>(a, opt, desc, t->state, rows_fixed, step_off);
+  else
+    train_chain_kernel<16><<<grid, kChainThreads, smem, s>>>(a, opt, desc, t->state, rows_fixed, step_off);
   SIMBA_CUDA_TRY(cudaGetLastError());
   return SIMBA_OK;
 }
@@ -996,7 +1029,8 @@ extern "C" int simba_trainer_validation(simba_trainer_t* t, const float* x, cons
     const int nr = (int)((rows - r0) < t->cap_rows ? (rows - r0) : t->cap_rows);
     int rc = enqueue_chain(t, x + r0 * t->IN, 0, y + r0 * t->O, 0, 0, nr, nr, nullptr, 0, nullptr, 0, s);
     if (rc) return rc;
-    const int tiles = (nr + kRows - 1) / kRows;
+    const int R = chain_tile_rows(t, nr);
+    const int tiles = (nr + R - 1) / R;
     val_accumulate_kernel<<<1, 32, 0, s>>>(t->partial, t->tiles_cap, tiles, t->E, t->val_acc,
                                            r0 == 0 ? 1 : 0);
   }
