@@ -91,6 +91,8 @@ struct simba_model {
   float* d_w_f32 = nullptr;
   float* d_bias_f32 = nullptr;
   void* d_w_bf16 = nullptr;
+  void* d_w_wide = nullptr;     // wide-model tcgen05 weight stream (rollout_tc_wide.cu)
+  int64_t w_wide_member_bytes = 0;
   float* d_bias_tc = nullptr;
   void* d_bias_k16 = nullptr;   // per member, per layer: UMMA B tile [128 n][16 k] (no swizzle) holding the bias as bf16 hi + lo
   float tc_scale_a[64] = {0}, tc_scale_b[64] = {0};
@@ -133,6 +135,7 @@ extern "C" int simba_model_create(const simba_model_config_t* cfg, simba_model_t
 
 static void model_free_device(simba_model* m) {
   cudaFree(m->d_w_f32); cudaFree(m->d_bias_f32); cudaFree(m->d_w_bf16); cudaFree(m->d_bias_tc); cudaFree(m->d_bias_k16);
+  cudaFree(m->d_w_wide); m->d_w_wide = nullptr;
   m->d_bias_tc = nullptr; m->d_bias_k16 = nullptr;
   cudaFree(m->d_smin); cudaFree(m->d_sdelta); cudaFree(m->d_sinv);
   m->d_w_f32 = m->d_bias_f32 = m->d_smin = m->d_sdelta = m->d_sinv = nullptr;
@@ -333,6 +336,61 @@ extern "C" int simba_model_commit(simba_model_t* m) {
     CUDA_TRY(cudaMemcpy(m->d_bias_k16, bk.data(), bk.size() * 2, cudaMemcpyHostToDevice));
   }
 
+  // ---- wide-model tcgen05 weight stream: per member the tiles of one rollout step in consumption
+  //      order — layer 0: one [U x 64] tile; layers 1..L-1: KA tiles [U x 64]; heads: KA tiles
+  //      [128 x 64] (mu rows [0, O), var rows [64, 64 + O)); each tile K-major SWIZZLE_128B. The bias
+  //      of a layer sits in k rows K_real (bf16 hi) and K_real + 1 (bf16 of the remainder), which the
+  //      kernel multiplies by constant ones in the A tile. -----------------------------------------
+  m->w_wide_member_bytes = 0;
+  if (rollout_tc_wide_supported(O, c.act_dim, L, U, 1)) {
+    const int KA = (U + 2 + 63) / 64;
+    const int64_t member_bytes = rollout_tc_wide_member_bytes(L, U);
+    std::vector<uint16_t> img((size_t)E * member_bytes / 2, 0);
+    auto split_bias = [&](float bv, uint16_t& hi, uint16_t& lo) {
+      hi = f32_to_bf16_rne(bv);
+      uint32_t hb = (uint32_t)hi << 16;
+      float hf;
+      memcpy(&hf, &hb, 4);
+      lo = f32_to_bf16_rne(bv - hf);
+    };
+    for (int e = 0; e < E; ++e) {
+      int64_t off = (int64_t)e * member_bytes;
+      for (int l = 0; l <= L; ++l) {
+        const int K = l == 0 ? IN : U;
+        const int rows = l < L ? U : 128;                  // tile rows = output features
+        const int tiles = l == 0 ? 1 : KA;
+        auto weight = [&](int k, int n) -> uint16_t {
+          int layer = l, col = n;                          // Keras layer index and output column
+          if (l == L) {
+            if (n < O) { layer = L; col = n; }
+            else if (n >= 64 && n < 64 + O) { layer = L + 1; col = n - 64; }
+            else return 0;
+          }
+          const int width = l < L ? U : O;
+          if (k < K) return f32_to_bf16_rne(m->kernels[e * (L + 2) + layer][(size_t)k * width + col]);
+          if (k == K || k == K + 1) {
+            uint16_t hi, lo;
+            split_bias(m->biases[e * (L + 2) + layer][col], hi, lo);
+            return k == K ? hi : lo;
+          }
+          return 0;
+        };
+        for (int tI = 0; tI < tiles; ++tI) {
+          for (int n = 0; n < rows; ++n)
+            for (int kk = 0; kk < 64; ++kk) {
+              const int chunk16 = kk / 8, within = kk % 8;
+              const int64_t byte = off + (int64_t)n * 128 + ((chunk16 ^ (n & 7)) * 16) + within * 2;
+              img[byte / 2] = weight(tI * 64 + kk, n);
+            }
+          off += (int64_t)rows * 128;
+        }
+      }
+    }
+    m->w_wide_member_bytes = member_bytes;
+    if (!m->d_w_wide) CUDA_TRY(cudaMalloc(&m->d_w_wide, img.size() * 2));
+    CUDA_TRY(cudaMemcpy(m->d_w_wide, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+  }
+
   // ---- scaler: delta = max - min, 1.01 where delta < 1e-5 (transition_model.py:85-86) ----------
   std::vector<float> delta(IN), inv(IN);
   for (int k = 0; k < IN; ++k) {
@@ -366,6 +424,8 @@ static void fill_model_params(const simba_model* m, RolloutParams& prm) {
   prm.act_rows = m->act_rows;
   prm.w_bf16 = m->d_w_bf16;
   prm.w_bf16_member_bytes = m->w_bf16_member_bytes;
+  prm.w_wide = m->d_w_wide;
+  prm.w_wide_member_bytes = m->w_wide_member_bytes;
   prm.bias_tc = m->d_bias_tc;
   prm.bias_k16 = m->d_bias_k16;
   memcpy(prm.tc_scale_a, m->tc_scale_a, sizeof(prm.tc_scale_a));
@@ -605,9 +665,11 @@ extern "C" int simba_planner_create(simba_model_t* model, const simba_planner_co
   if (cfg->precision != SIMBA_PREC_FP32 && cfg->precision != SIMBA_PREC_BF16_TC)
     return fail(SIMBA_ERR_BAD_CONFIG, "precision %d unknown", cfg->precision);
   if (cfg->precision == SIMBA_PREC_BF16_TC &&
-      !rollout_tc_supported(mc.obs_dim, mc.act_dim, mc.n_layers, mc.units, cfg->horizon))
+      !rollout_tc_supported(mc.obs_dim, mc.act_dim, mc.n_layers, mc.units, cfg->horizon) &&
+      !rollout_tc_wide_supported(mc.obs_dim, mc.act_dim, mc.n_layers, mc.units, cfg->horizon))
     return fail(SIMBA_ERR_UNSUPPORTED,
-                "bf16 tcgen05 rollout covers units == 128, obs_dim <= 60, obs_dim+act_dim <= 64; "
+                "bf16 tcgen05 rollout covers units == 128 (obs_dim <= 60, obs_dim+act_dim <= 64) and "
+                "wide models with 128 < units <= 440, units %% 16 == 0, obs_dim+act_dim <= 62; "
                 "use precision fp32 for this shape");
   int rc = validate_scorer(cfg->scorer, mc.obs_dim);
   if (rc != SIMBA_OK) return rc;
@@ -625,7 +687,7 @@ extern "C" int simba_planner_create(simba_model_t* model, const simba_planner_co
   if (rc != SIMBA_OK) { delete p; return rc; }
   p->tile_rows = cfg->precision == SIMBA_PREC_BF16_TC ? kTcTileRows : kF32TileRows;
   build_tiles(p->geom, p->tile_rows, p->tiles);
-  if (cfg->precision == SIMBA_PREC_BF16_TC && p->tiles.size() > 148) {
+  if (cfg->precision == SIMBA_PREC_BF16_TC && mc.units == 128 && p->tiles.size() > 148) {
     // more tiles than SMs: two tiles per CTA so one tile's MMAs overlap the other's epilogue
     p->tiles_per_cta = 2;
     build_tiles(p->geom, p->tile_rows, p->tiles, 2);
@@ -785,9 +847,12 @@ static int do_rollout_score(simba_planner_t* p, const float* states, const float
   prm.pdl = pdl ? 1 : 0;
   if (const char* tlp = getenv("SIMBA_TC_TIMELINE_PTR"))   // debug builds only (tools/tc_timeline.py)
     prm.traj_out = reinterpret_cast<float*>(strtoull(tlp, nullptr, 10));
-  if (p->cfg.precision == SIMBA_PREC_BF16_TC)
-    CUDA_TRY(launch_rollout_tc(prm, prm.n_tiles, (cudaStream_t)stream));
-  else
+  if (p->cfg.precision == SIMBA_PREC_BF16_TC) {
+    if (p->model->cfg.units == 128)
+      CUDA_TRY(launch_rollout_tc(prm, prm.n_tiles, (cudaStream_t)stream));
+    else
+      CUDA_TRY(launch_rollout_tc_wide(prm, prm.n_tiles, (cudaStream_t)stream));
+  } else
     CUDA_TRY(launch_rollout_f32(prm, prm.n_tiles, (cudaStream_t)stream));
   return SIMBA_OK;
 }

@@ -22,6 +22,10 @@ struct RolloutParams {
   // bf16 image: per member, per layer pre-swizzled UMMA B tiles (see pack_bf16 in api.cu)
   const void* w_bf16;
   int64_t w_bf16_member_bytes;
+  // wide models (128 < units <= 440): per member the per-step stream of UMMA weight tiles in
+  // consumption order, biases in the K padding (see rollout_tc_wide.cu)
+  const void* w_wide;
+  int64_t w_wide_member_bytes;
   const void* bias_k16;       // [E][L+1][4096 B] bias K-blocks (see simba_model_commit)
   const float* bias_tc;       // [E][L+1][128] fp32 (heads: mu bias at [0, O), var bias at [64, 64+O))
   int32_t tc_tiles_per_cta;   // 1 (latency: small populations) or 2 (MMA / epilogue ping-pong)
@@ -61,5 +65,8 @@ size_t rollout_f32_smem_bytes(const RolloutParams& prm);
 cudaError_t launch_rollout_f32(const RolloutParams& prm, int n_tiles, cudaStream_t stream);
 cudaError_t launch_rollout_tc(const RolloutParams& prm, int n_tiles, cudaStream_t stream);
 bool rollout_tc_supported(int O, int A, int L, int U, int H);
+cudaError_t launch_rollout_tc_wide(const RolloutParams& prm, int n_tiles, cudaStream_t stream);
+bool rollout_tc_wide_supported(int O, int A, int L, int U, int H);
+int64_t rollout_tc_wide_member_bytes(int L, int U);
 
 }  // namespace simba
