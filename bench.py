@@ -173,7 +173,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
-    ap.add_argument('--extras', default=None, help="comma list of: c3, c4, fp32, train (default: c3 when N > 1, c4,c3,train when N == 1)")
+    ap.add_argument('--extras', default=None, help="comma list of: c3, c4, c5, fp32, train (default: c3 when N > 1, c4,c3,c5,train when N == 1)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -327,7 +327,7 @@ def main():
     # ---- extras -----------------------------------------------------------------------------------
     extras = {}
     if args.extras is None:
-        args.extras = 'c3' if world > 1 else 'c4,c3,train'
+        args.extras = 'c3' if world > 1 else 'c4,c3,c5,train'
     want = [x for x in args.extras.split(',') if x]
     try:
         if 'fp32' in want and precision != 'fp32':
@@ -336,6 +336,8 @@ def main():
             extras['c4'] = bench_batched(synthetic, torch, precision, flush, world, rank)
         if 'c3' in want:
             extras['c3'] = bench_c3(synthetic, torch, dist, lib, _lib, precision, world, rank)
+        if 'c5' in want and rank == 0:
+            extras['c5'] = bench_wide(synthetic, torch, flush)
         if 'train' in want and rank == 0:
             extras['train'] = bench_train(torch, cpu=not args.no_cpu_baseline and world == 1)
     except Exception as e:                      # extras never take the headline line down
@@ -374,6 +376,35 @@ def bench_plain(synthetic, torch, c, precision, states, flush, K):
     torch.cuda.synchronize()
     ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     return {"plans_per_s": 1e3 / ms, "ms_per_plan": ms, "precision": precision}
+
+
+def bench_wide(synthetic, torch, flush):
+    """BASELINE configs[4]: the wide 10 x (4 x 400) ensemble, horizon 50 — single-state plans on the
+    streaming tcgen05 kernel (bf16) and on the fp32 kernel, plus 5 states per call (150 row tiles = one
+    wave) for the kernel's throughput."""
+    out = {}
+    fpt = None
+    for precision, S in (('bf16', 1), ('fp32', 1), ('bf16', 5)):
+        c = synthetic.make_workload('c5', S=S, seed=0)
+        pol = synthetic.build_policy(c, 'penalty', precision=precision, seed=31)
+        st = torch.from_numpy(synthetic.make_state(c['sensors'], seed=500, n_states=S).reshape(S, -1)).cuda()
+        pol.plan_device(st)
+        torch.cuda.synchronize()
+        K = 3
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for k in range(K):
+            flush.fill_(k & 0xff)
+            ev[k][0].record()
+            pol.plan_device(st)
+            ev[k][1].record()
+        torch.cuda.synchronize()
+        ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+        fpt = synthetic.flops_per_transition(c['O'], c['A'], c['L'], c['U'])
+        trans = c['I'] * c['H'] * c['P'] * c['N'] * S
+        out["%s_%dstate" % (precision, S)] = {"ms_per_call": ms, "plans_per_s": S * 1e3 / ms,
+                                              "tflops": trans * fpt / (ms * 1e-3) / 1e12}
+    out["workload"] = "configs[4]: E=10 L=4x400 O=60 A=2 H=50 N=150 P=20 I=5; %d flop per transition" % fpt
+    return out
 
 
 def bench_train(torch, cpu=True, steps=1000, rows=24000):

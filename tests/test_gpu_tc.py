@@ -53,9 +53,12 @@ def test_tc_rollout_rows_close_to_oracle(cfg, over):
     assert np.max(np.abs(cand_got - cand_ref)) < 2e-2
 
 
-def test_tc_plan_close_to_oracle_and_fp32():
+@pytest.mark.parametrize("cfg,over", [('c1', {}), ('c1', dict(U=400, E=2, H=8)), ('c5', dict(H=12, E=5))])
+def test_tc_plan_close_to_oracle_and_fp32(cfg, over):
+    """Whole plans: the bf16 kernels (units 128: rollout_tc.cu; wide: rollout_tc_wide.cu) against the
+    fp32 kernel on the same draws."""
     from simba_b200 import _lib, synthetic
-    c = helpers.workload('c1')
+    c = helpers.workload(cfg, **over)
     z, eps, zf = synthetic.make_draws(c['I'], 1, c['N'], c['H'], c['A'], c['P'], c['O'])
     res = {}
     for precision in ('fp32', 'bf16'):
