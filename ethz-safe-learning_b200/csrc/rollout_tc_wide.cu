@@ -416,26 +416,45 @@ __global__ void __launch_bounds__(kWideThreads, 1) rollout_tc_wide_kernel(const 
       if (cgp == 0) combine(rs.dist, rs.cost);
 
       const int n_chunks = U >> 3;                       // 16-byte chunks per hidden activation row
+      const int my_c0 = cgp * (n_chunks / kQ) + min(cgp, n_chunks % kQ);
+      const int my_c1 = my_c0 + n_chunks / kQ + (cgp < n_chunks % kQ ? 1 : 0);
       for (int t = 0; t < H; ++t) {
         prefetch_actions(t + 1);
         // ---- hidden layers: TMEM -> ReLU -> bf16 -> swizzled A tile (bias is in the accumulator) ----
         for (int l = 0; l < L; ++l) {
           wait_accumulator();
-          // chunks cgp, cgp + kQ, ... of this row, four TMEM loads in flight at a time
-          for (int c0 = cgp; c0 < n_chunks; c0 += 4 * kQ) {
-            uint32_t v[4][8];
+          // this column group's contiguous run of 16-byte chunks, eight chunks (64 columns = two
+          // 32-column TMEM loads) in flight at a time
+          for (int c0 = my_c0; c0 < my_c1; c0 += 8) {
+            uint32_t v[2][32];
+            const bool two = c0 + 8 <= my_c1, one = c0 + 4 <= my_c1;
+            if (one) {
+              tmem_ld<32>(t_lane + (uint32_t)c0 * 8, v[0]);
+              if (two) tmem_ld<32>(t_lane + (uint32_t)(c0 + 4) * 8, v[1]);
+              tmem_ld_wait();
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (c0 + u * kQ < n_chunks) tmem_ld<8>(t_lane + (uint32_t)(c0 + u * kQ) * 8, v[u]);
-            tmem_ld_wait();
+              for (int h = 0; h < 2; ++h) {
+                if (h == 1 && !two) break;
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (c0 + u * kQ < n_chunks)
-                st_shared_v4(a_chunk(c0 + u * kQ),
-                             pack_relu_bf16(__uint_as_float(v[u][0]), __uint_as_float(v[u][1])),
-                             pack_relu_bf16(__uint_as_float(v[u][2]), __uint_as_float(v[u][3])),
-                             pack_relu_bf16(__uint_as_float(v[u][4]), __uint_as_float(v[u][5])),
-                             pack_relu_bf16(__uint_as_float(v[u][6]), __uint_as_float(v[u][7])));
+                for (int u = 0; u < 4; ++u)
+                  st_shared_v4(a_chunk(c0 + h * 4 + u),
+                               pack_relu_bf16(__uint_as_float(v[h][u * 8 + 0]), __uint_as_float(v[h][u * 8 + 1])),
+                               pack_relu_bf16(__uint_as_float(v[h][u * 8 + 2]), __uint_as_float(v[h][u * 8 + 3])),
+                               pack_relu_bf16(__uint_as_float(v[h][u * 8 + 4]), __uint_as_float(v[h][u * 8 + 5])),
+                               pack_relu_bf16(__uint_as_float(v[h][u * 8 + 6]), __uint_as_float(v[h][u * 8 + 7])));
+              }
+            }
+            // tail: up to three single chunks
+            const int done = two ? 8 : (one ? 4 : 0);
+            for (int c = c0 + done; c < my_c1 && c < c0 + 8; ++c) {
+              uint32_t w[8];
+              tmem_ld<8>(t_lane + (uint32_t)c * 8, w);
+              tmem_ld_wait();
+              st_shared_v4(a_chunk(c), pack_relu_bf16(__uint_as_float(w[0]), __uint_as_float(w[1])),
+                           pack_relu_bf16(__uint_as_float(w[2]), __uint_as_float(w[3])),
+                           pack_relu_bf16(__uint_as_float(w[4]), __uint_as_float(w[5])),
+                           pack_relu_bf16(__uint_as_float(w[6]), __uint_as_float(w[7])));
+            }
           }
           publish_a();
           if (prm.sampling_propagation) {
