@@ -8,17 +8,20 @@
 //   * one CTA = one ensemble member x NTILES row tiles of 128 rollouts; the member's whole bf16
 //     weight set (144 KB for 4x128) is staged ONCE in shared memory by the TMA engine
 //     (cp.async.bulk of pre-swizzled UMMA images) and reused for all H steps x (L+1) layers;
-//   * activations are the A operand. Q epilogue threads share one rollout row (Q = 4: latency
-//     configuration for small populations, Q = 2 with two tiles per CTA: throughput configuration):
-//     each reads its column slice of the fp32 accumulator row from TMEM (tcgen05.ld 32x32b), applies
-//     bias + ReLU, packs bf16 and stores straight into the 128B-swizzled K-major A tile of the next
-//     layer; the thread count per SM sub-partition (4 warps) is what hides the MUFU / TMEM latencies;
-//   * per tile and layer: the tile's threads write the A tile, fence it to the async proxy and meet
-//     at a named barrier (bar.sync, tile threads only); one elected thread of the tile then issues
-//     tcgen05.mma (M=128, N=128, K=16 per instruction, fp32 accumulate in TMEM) and tcgen05.commit
-//     onto the tile's "accumulator ready" mbarrier, on which all threads of the tile wait. There is
-//     no separate MMA warp to wake up; with two tiles per CTA the tensor pipe works on one tile
-//     while the other tile's threads run their epilogue;
+//   * activations are the A operand and live in TENSOR MEMORY (TS-mode tcgen05.mma: A from TMEM,
+//     B = weights from shared memory), so an MMA streams only the weight tile from SMEM. Q epilogue
+//     threads share one rollout row (Q = 4: latency configuration for small populations, Q = 2
+//     with two tiles per CTA: throughput configuration): each reads its column slice of the fp32
+//     accumulator row from TMEM (tcgen05.ld 32x32b), applies ReLU, packs bf16 and writes the next
+//     layer's A operand back into the tile's A columns (tcgen05.st); the thread count per SM
+//     sub-partition (4 warps) is what hides the MUFU / TMEM latencies. The bias of every layer is
+//     one more K = 16 MMA (constant ones tile x [bf16(b), bf16(b - hi)] block, both from SMEM);
+//   * per tile and layer: the tile's threads wait for their A-operand stores (tcgen05.wait::st),
+//     fence and meet at a named barrier (bar.sync, tile threads only); one elected thread of the
+//     tile then issues tcgen05.mma (M=128, N=128, K=16 per instruction, fp32 accumulate in TMEM)
+//     and tcgen05.commit onto the tile's "accumulator ready" mbarrier, on which the tile's threads
+//     wait. There is no separate MMA warp to wake up; with two tiles per CTA the tensor pipe works
+//     on one tile while the other tile's threads run their epilogue;
 //   * the rollout state s_t (fp32) lives in spare TMEM columns next to the accumulators, so it costs
 //     no registers between steps. The Gaussian-head epilogue is ONE pass over 16-wide column chunks:
 //     load mu / raw-var accumulators and the state chunk from TMEM, softplus, sqrt, Philox4x32-10 +
