@@ -114,3 +114,30 @@ def test_tc_two_tiles_per_cta_matches_one_tile():
         outs.append(ret.cpu().numpy().reshape(cc['P'], n_take))
     assert np.all(np.isfinite(outs[0]))
     assert np.array_equal(outs[0][:, :500], outs[1])
+
+
+def test_tc_wide_batched_states_philox_and_early_exit():
+    """The wide (units = 400) kernel in production mode: Philox draws on the device, several states
+    per call (tiles that straddle states), reproducible, equal to per-state plans fed with the same
+    Philox contract draws (bf16 tolerance), and the early break (cem_mpc.py:66-67) skips work."""
+    from oracle import philox
+    c = helpers.workload('tiny', U=400, L=2, S=3)
+    pol_b = helpers.cuda_policy(c, 'penalty', precision='bf16')
+    acts_b, scores_b = pol_b.do_generate_action(c['state'], seed=11)
+    again, _ = pol_b.do_generate_action(c['state'], seed=11)
+    assert np.array_equal(acts_b, again)
+    c1 = dict(c); c1['S'] = 1
+    for s in range(3):
+        pol = helpers.cuda_policy(c1, 'penalty', precision='bf16')
+        z = np.stack([philox.action_normals(11, it, c['N'], c['H'], c['A'], state_index=s)
+                      for it in range(c['I'])])[:, None]
+        B = c['P'] * c['N']
+        eps = np.stack([philox.noise_normals(11, it, c['H'], np.arange(B), c['O'], state_index=s)
+                        for it in range(c['I'])])[:, None]
+        zf = philox.final_normals(11, c['A'], state_index=s)[None]
+        pol.set_external_draws(z, eps, zf)
+        a, sc = pol.do_generate_action(c['state'][s])
+        assert abs(sc - scores_b[s]) < 5e-2
+    pol_e = helpers.cuda_policy(c, 'penalty', precision='bf16', stddev_threshold=0.9)
+    pol_e.do_generate_action(c['state'], seed=11)
+    assert np.all(pol_e.iterations_run == 1)
