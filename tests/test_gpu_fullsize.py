@@ -1,0 +1,65 @@
+"""BASELINE.json's full sizes through size-independent properties (the oracle cannot run these in
+seconds): determinism, top-K consistency of the elite set, refit == moments of the elite actions,
+best-so-far monotonicity, and batched == independent plans at 1024 states per call."""
+import numpy as np
+import pytest
+
+from oracle import philox
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def test_c3_full_population_plan_properties():
+    """configs[2]: population 65536, 32 particles, horizon 30, K = 6554, on one GPU (bf16 kernel,
+    cluster select / refit kernels)."""
+    from simba_b200 import _lib
+    c = helpers.workload('c3')
+    pol = helpers.cuda_policy(c, 'penalty', precision='bf16', member_map='particle')
+    a1, s1 = pol.do_generate_action(c['state'], seed=3)
+    N, K, H, A = c['N'], c['K'], c['H'], c['A']
+    elite = pol.buffer(_lib.BUF_ELITE, torch.int32).cpu().numpy()
+    pairs = pol.buffer(_lib.BUF_PAIRS_LOCAL).cpu().numpy().reshape(N, 2)     # world_size 1: local == all
+    acts = pol.buffer(_lib.BUF_ACTIONS).cpu().numpy().reshape(N, H, A)
+    mu = pol.buffer(_lib.BUF_MU).cpu().numpy().reshape(H, A)
+    sigma = pol.buffer(_lib.BUF_SIGMA).cpu().numpy().reshape(H, A)
+    a2, s2 = pol.do_generate_action(c['state'], seed=3)
+    assert np.array_equal(a1, a2) and s1 == s2                          # deterministic end to end
+    assert int(pol.iterations_run[0]) == c['I']
+    # the elite set is exactly the stable top-K of the device's own (return, cost) pairs
+    scores = pairs[:, 0] - (pairs[:, 1] > pol.count_threshold).astype(np.float32) * np.float32(100)
+    order = np.argsort(-scores, kind='stable')
+    assert elite.shape == (K,) and np.array_equal(elite, np.sort(order[:K]))
+    assert np.all(np.diff(elite) > 0)
+    # refit (smoothing 0): population moments of the elite action sequences
+    sel = acts[elite].astype(np.float64)
+    assert np.allclose(mu, sel.mean(0), rtol=1e-5, atol=1e-6)
+    assert np.allclose(sigma, np.sqrt(sel.var(0)), rtol=1e-4, atol=1e-6)
+    assert np.all(np.abs(acts) <= 1.0)                                  # clip_by_value to the action box
+    # best-so-far can only be at least the last iteration's best candidate
+    assert s1 >= scores.max() - 1e-6
+    assert np.all(np.abs(a1) <= 1.0 + 0.06)                             # + N(0, 0.01) final noise
+
+
+def test_c4_1024_states_per_call_equal_independent_plans():
+    """configs[3]: 1024 states per call (tiles straddle states) against single-state plans fed with the
+    Philox contract draws of the same (seed, state index); bf16 kernel on both sides."""
+    S = 1024
+    c = helpers.workload('c1', S=S)
+    pol = helpers.cuda_policy(c, 'penalty', precision='bf16', n_states=S)
+    acts_b, scores_b = pol.do_generate_action(c['state'], seed=11)
+    assert acts_b.shape == (S, c['A']) and np.all(np.isfinite(acts_b)) and np.all(np.isfinite(scores_b))
+    assert np.all(pol.iterations_run == c['I'])
+    c1 = dict(c); c1['S'] = 1
+    B = c['P'] * c['N']
+    for s in (0, 517, S - 1):
+        p1 = helpers.cuda_policy(c1, 'penalty', precision='bf16')
+        z = np.stack([philox.action_normals(11, it, c['N'], c['H'], c['A'], state_index=s)
+                      for it in range(c['I'])])[:, None]
+        eps = np.stack([philox.noise_normals(11, it, c['H'], np.arange(B), c['O'], state_index=s)
+                        for it in range(c['I'])])[:, None]
+        zf = philox.final_normals(11, c['A'], state_index=s)[None]
+        p1.set_external_draws(z, eps, zf)
+        a, sc = p1.do_generate_action(c['state'][s])
+        assert abs(sc - scores_b[s]) < 5e-2, (s, sc, scores_b[s])
