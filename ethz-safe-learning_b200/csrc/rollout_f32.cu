@@ -275,12 +275,12 @@ size_t rollout_f32_smem_bytes(const RolloutParams& prm) {
 cudaError_t launch_rollout_f32(const RolloutParams& prm, int n_tiles, cudaStream_t stream) {
   if (n_tiles == 0) return cudaSuccess;
   const size_t smem = rollout_f32_smem_bytes(prm);
-  static size_t configured = 0;
-  if (smem > configured) {
+  // set on every launch: the attribute is per device and per function, and launches happen only at
+  // graph capture or in the non-graph entry points, never on the replayed hot path
+  {
     cudaError_t e = cudaFuncSetAttribute(rollout_f32_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   rollout_f32_kernel<<<n_tiles, NT, smem, stream>>>(prm);
   return cudaGetLastError();

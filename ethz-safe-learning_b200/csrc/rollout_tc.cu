@@ -568,12 +568,12 @@ static size_t tc_smem_bytes(int L, int ntiles, int q, int nparts) {
 template <int NTILES, int Q>
 static cudaError_t launch_variant(const RolloutParams& prm, int n_tiles, cudaStream_t stream) {
   const size_t smem = tc_smem_bytes(prm.L, NTILES, Q, 1 + prm.scorer.n_constraints);
-  static size_t configured = 0;
-  if (smem > configured) {
+  // set on every launch: the attribute is per device and per function, and launches happen only at
+  // graph capture or in the non-graph entry points, never on the replayed hot path
+  {
     cudaError_t e = cudaFuncSetAttribute(rollout_tc_kernel<NTILES, Q>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   const int grid = (n_tiles + NTILES - 1) / NTILES;
   cudaLaunchConfig_t cfg{};

@@ -525,12 +525,12 @@ static size_t wide_smem_bytes(int L, int U, int nparts) {
 cudaError_t launch_rollout_tc_wide(const RolloutParams& prm, int n_tiles, cudaStream_t stream) {
   if (n_tiles == 0) return cudaSuccess;
   const size_t smem = wide_smem_bytes(prm.L, prm.U, 1 + prm.scorer.n_constraints);
-  static size_t configured = 0;
-  if (smem > configured) {
+  // set on every launch: the attribute is per device and per function, and launches happen only at
+  // graph capture or in the non-graph entry points, never on the replayed hot path
+  {
     cudaError_t e = cudaFuncSetAttribute(rollout_tc_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(n_tiles);

@@ -264,7 +264,8 @@ typedef struct simba_trainer_config {
   float clipvalue;           /* mlp_ensemble.py:116 (1.0); <= 0 disables clipping               */
 } simba_trainer_config_t;
 
-/* Copies the model's current (set_layer) weights as fp32 master weights; Adam state zeroed. */
+/* Copies the model's current (set_layer) weights as fp32 master weights; Adam state zeroed. The
+ * model handle must outlive the trainer (simba_trainer_sync_model writes back into it). */
 int simba_trainer_create(simba_model_t* m, const simba_trainer_config_t* cfg, simba_trainer_t** out);
 int simba_trainer_destroy(simba_trainer_t* t);
 /* MlpEnsemble.training_step — mlp_ensemble.py:134-146. x DEVICE [E, rows, O+A] (already scaled),
