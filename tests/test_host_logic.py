@@ -138,3 +138,79 @@ def test_weight_handoff_npz_round_trip(tmp_path):
         c.load(path)
     a.save()          # the reference's argument-less stubs stay no-ops
     a.load()
+
+
+class _CountingEnv(object):
+    """Deterministic environment for the collection loops (no GPU needed)."""
+
+    def __init__(self, length, goal_at=None):
+        from simba_b200.spaces import Box
+        self.action_space = Box([-1.0, -1.0], [1.0, 1.0])
+        self.length, self.goal_at = length, goal_at
+        self.resets = 0
+
+    def reset(self):
+        self.t = 0
+        self.resets += 1
+        return np.full(3, float(self.resets), np.float32)
+
+    def step(self, action):
+        self.t += 1
+        info = dict(cost=1.0, goal_met=(self.goal_at is not None and self.t == self.goal_at))
+        return np.full(3, self.resets + 0.01 * self.t, np.float32), float(action[0]), self.t >= self.length, info
+
+
+class _EchoPolicy(object):
+    def __init__(self):
+        self.shapes = []
+
+    def generate_action(self, state):
+        state = np.asarray(state)
+        self.shapes.append(state.shape)
+        if state.ndim == 1:
+            return np.array([0.5, -0.5], np.float32)
+        return np.tile(np.array([0.5, -0.5], np.float32), (state.shape[0], 1))
+
+
+def test_collection_loops_follow_the_reference_semantics():
+    """agent.py:83-153: action_repeat accumulates reward and cost, an episode ends at max length or
+    done, goal_met ends the repeat early, collection stops once the finished paths hold batch_size steps;
+    the vectorised loop issues one batched call per decision and matches the single-env loop for n = 1."""
+    from simba_b200 import agents
+    env, pol = _CountingEnv(length=7, goal_at=2), _EchoPolicy()
+    path, steps = agents.sample_trajectory(env, pol, max_trajectory_length=100, action_repeat=3)
+    assert steps == 7 and path['terminal'][-1] == 1.0 and path['terminal'][:-1].sum() == 0
+    # decisions: steps 1-2 (goal_met at t = 2 stops the repeat), 3-5, 6-7 (done)
+    assert [i['cost'] for i in path['info']] == [2.0, 3.0, 2.0]
+    assert np.allclose(path['reward'], [1.0, 1.5, 1.0]) and path['action'].shape == (3, 2)
+    path, steps = agents.sample_trajectory(_CountingEnv(length=50), pol, max_trajectory_length=8, action_repeat=3)
+    assert steps == 8 and len(path['reward']) == 3                      # cut at max_trajectory_length
+    a_paths, a_steps = agents.sample_trajectories(_CountingEnv(length=5), _EchoPolicy(), 12, 100, 2)
+    b_paths, b_steps = agents.sample_trajectories_vectorized([_CountingEnv(length=5)], _EchoPolicy(), 12, 100, 2)
+    assert a_steps == b_steps == 15 and len(a_paths) == len(b_paths) == 3
+    for x, y in zip(a_paths, b_paths):
+        for key in ('observation', 'action', 'reward', 'next_observation', 'terminal'):
+            assert np.array_equal(x[key], y[key])
+    vec_pol = _EchoPolicy()
+    envs = [_CountingEnv(length=4 + i) for i in range(3)]
+    paths, steps = agents.sample_trajectories_vectorized(envs, vec_pol, 20, 100, 1)
+    assert steps >= 20 and steps == sum(len(p['reward']) for p in paths)
+    assert all(shape == (3, 3) for shape in vec_pol.shapes)              # one batched call per decision
+    assert sorted({len(p['reward']) for p in paths}) == [4, 5, 6]
+
+
+def test_random_mpc_and_batch_schedule_host_logic():
+    from simba_b200.models import MlpEnsemble
+    from simba_b200.policies import RandomMpc
+    from simba_b200.spaces import Box
+    a = np.array([RandomMpc(Box([-1.0, 0.0], [1.0, 2.0])).generate_action(None) for _ in range(100)])
+    assert a[:, 0].min() >= -1 and a[:, 1].min() >= 0 and a[:, 1].max() <= 2
+    ens = MlpEnsemble(12, 10, 3, batch_size=16, mlp_params=dict(n_layers=1, units=8))
+    np.random.seed(0)
+    index, rows = ens.batch_schedule(50, 9)                               # mlp_ensemble.py:172-186
+    assert index.shape == (9, 3, 16) and rows.tolist() == [13, 13, 12, 12, 13, 13, 12, 12, 13]
+    for e in range(3):                                                    # one permutation per member per pass
+        first = np.concatenate([index[s, e, :rows[s]] for s in range(4)])
+        assert sorted(first.tolist()) == list(range(50))
+    tr, va = ens._split_indices(50)
+    assert len(va) == 10 and len(tr) == 40 and sorted(np.concatenate([tr, va]).tolist()) == list(range(50))
