@@ -4,7 +4,8 @@ every GEMM (fp32 accumulate), Box-Muller / softplus use the MUFU approximations.
 
 Stated tolerance (external draws, C1 dims, H = 15):
   * per-candidate mean return:   |device - oracle| <= 2e-2 absolute (returns are O(1))
-  * per-row cost-mask agreement: >= 97 % of rows identical (threshold flips near 0.2 / 0.24)
+  * per-row cost-mask agreement: >= 1 - 0.002 * H of the rows identical, i.e. 97 % at H = 15 (a row's
+    mask has one bit per step; a threshold flip near 0.2 / 0.24 in any step makes the row differ)
   * plan score vs the fp32 kernel: <= 5e-2 absolute
 """
 import numpy as np
@@ -20,7 +21,7 @@ torch = pytest.importorskip("torch")
 @pytest.mark.parametrize("cfg,over", [('tiny', {}), ('c1', {}), ('tiny', dict(S=1, N=700, P=8, E=2, K=10)),
                                       # wide models: the streaming tcgen05 kernel (rollout_tc_wide.cu)
                                       ('tiny', dict(U=400, L=2)), ('tiny', dict(U=256, L=3, N=100)),
-                                      ('tiny', dict(U=144, L=4)), ('c5', dict(H=10))])
+                                      ('tiny', dict(U=144, L=4)), ('c5', dict(H=10)), ('c5', {})])
 def test_tc_rollout_rows_close_to_oracle(cfg, over):
     from simba_b200 import _lib
     lib = _lib.load()
@@ -47,7 +48,7 @@ def test_tc_rollout_rows_close_to_oracle(cfg, over):
           % (err.max(), err.mean(), agree, cum0.min(), cum0.max()))
     assert np.all(np.isfinite(got))
     assert err.mean() < 1e-2
-    assert agree > 0.97
+    assert agree > 1.0 - 0.002 * c['H']
     cand_got = got.reshape(c['P'], c['N']).mean(0)
     cand_ref = cum0.reshape(c['P'], c['N']).mean(0)
     assert np.max(np.abs(cand_got - cand_ref)) < 2e-2
