@@ -276,7 +276,8 @@ extern "C" int simba_model_commit(simba_model_t* m) {
   m->w_bf16_member_bytes = 0;
   if (rollout_tc_supported(O, c.act_dim, L, U, 1)) {
     int64_t member_bytes = 0;
-    for (int l = 0; l <= L; ++l) member_bytes += bf16_layer_bytes(l == 0 ? IN : U);
+    // hidden / head layers always occupy K = 128 (two atoms): narrower models are zero-padded
+    for (int l = 0; l <= L; ++l) member_bytes += bf16_layer_bytes(l == 0 ? IN : 128);
     std::vector<uint16_t> img((size_t)E * member_bytes / 2, 0);
     for (int e = 0; e < E; ++e) {
       int64_t off = (int64_t)e * member_bytes;
@@ -289,7 +290,8 @@ extern "C" int simba_model_commit(simba_model_t* m) {
           if (n >= 64 && n < 64 + O) return m->kernels[e * (L + 2) + L + 1][(size_t)k * O + (n - 64)];
           return 0.0f;
         };
-        const int atoms = round_up(K, 64) / 64;
+        const int Kp = l == 0 ? IN : 128;
+        const int atoms = round_up(Kp, 64) / 64;
         for (int at = 0; at < atoms; ++at)
           for (int n = 0; n < 128; ++n)
             for (int kk = 0; kk < 64; ++kk) {
@@ -298,7 +300,7 @@ extern "C" int simba_model_commit(simba_model_t* m) {
                                    ((chunk16 ^ (n & 7)) * 16) + within * 2;
               img[byte / 2] = f32_to_bf16_rne(weight(at * 64 + kk, n));
             }
-        off += bf16_layer_bytes(K);
+        off += bf16_layer_bytes(Kp);
       }
     }
     m->w_bf16_member_bytes = member_bytes;
@@ -343,8 +345,9 @@ extern "C" int simba_model_commit(simba_model_t* m) {
   //      kernel multiplies by constant ones in the A tile. -----------------------------------------
   m->w_wide_member_bytes = 0;
   if (rollout_tc_wide_supported(O, c.act_dim, L, U, 1)) {
-    const int KA = (U + 2 + 63) / 64;
-    const int64_t member_bytes = rollout_tc_wide_member_bytes(L, U);
+    const int UP = rollout_tc_wide_units(U);               // kernel width: U zero-padded to 16
+    const int KA = (UP + 2 + 63) / 64;
+    const int64_t member_bytes = rollout_tc_wide_member_bytes(L, UP);
     std::vector<uint16_t> img((size_t)E * member_bytes / 2, 0);
     auto split_bias = [&](float bv, uint16_t& hi, uint16_t& lo) {
       hi = f32_to_bf16_rne(bv);
@@ -356,8 +359,9 @@ extern "C" int simba_model_commit(simba_model_t* m) {
     for (int e = 0; e < E; ++e) {
       int64_t off = (int64_t)e * member_bytes;
       for (int l = 0; l <= L; ++l) {
-        const int K = l == 0 ? IN : U;
-        const int rows = l < L ? U : 128;                  // tile rows = output features
+        const int K = l == 0 ? IN : U;                     // real input width
+        const int KB = l == 0 ? IN : UP;                   // the A tile holds the constant ones at k = KB, KB + 1
+        const int rows = l < L ? UP : 128;                 // tile rows = output features
         const int tiles = l == 0 ? 1 : KA;
         auto weight = [&](int k, int n) -> uint16_t {
           int layer = l, col = n;                          // Keras layer index and output column
@@ -365,13 +369,15 @@ extern "C" int simba_model_commit(simba_model_t* m) {
             if (n < O) { layer = L; col = n; }
             else if (n >= 64 && n < 64 + O) { layer = L + 1; col = n - 64; }
             else return 0;
+          } else if (n >= U) {
+            return 0;                                      // padded hidden unit: weights and bias 0
           }
           const int width = l < L ? U : O;
           if (k < K) return f32_to_bf16_rne(m->kernels[e * (L + 2) + layer][(size_t)k * width + col]);
-          if (k == K || k == K + 1) {
+          if (k == KB || k == KB + 1) {
             uint16_t hi, lo;
             split_bias(m->biases[e * (L + 2) + layer][col], hi, lo);
-            return k == K ? hi : lo;
+            return k == KB ? hi : lo;
           }
           return 0;
         };
@@ -668,8 +674,8 @@ extern "C" int simba_planner_create(simba_model_t* model, const simba_planner_co
       !rollout_tc_supported(mc.obs_dim, mc.act_dim, mc.n_layers, mc.units, cfg->horizon) &&
       !rollout_tc_wide_supported(mc.obs_dim, mc.act_dim, mc.n_layers, mc.units, cfg->horizon))
     return fail(SIMBA_ERR_UNSUPPORTED,
-                "bf16 tcgen05 rollout covers units == 128 (obs_dim <= 60, obs_dim+act_dim <= 64) and "
-                "wide models with 128 < units <= 440, units %% 16 == 0, obs_dim+act_dim <= 62; "
+                "bf16 tcgen05 rollout covers units <= 128 (obs_dim <= 60, obs_dim+act_dim <= 64) and "
+                "wide models with 128 < units <= 440 (obs_dim+act_dim <= 62, 2..6 layers); "
                 "use precision fp32 for this shape");
   int rc = validate_scorer(cfg->scorer, mc.obs_dim);
   if (rc != SIMBA_OK) return rc;
@@ -687,7 +693,7 @@ extern "C" int simba_planner_create(simba_model_t* model, const simba_planner_co
   if (rc != SIMBA_OK) { delete p; return rc; }
   p->tile_rows = cfg->precision == SIMBA_PREC_BF16_TC ? kTcTileRows : kF32TileRows;
   build_tiles(p->geom, p->tile_rows, p->tiles);
-  if (cfg->precision == SIMBA_PREC_BF16_TC && mc.units == 128 && p->tiles.size() > 148) {
+  if (cfg->precision == SIMBA_PREC_BF16_TC && mc.units <= 128 && p->tiles.size() > 148) {
     // more tiles than SMs: two tiles per CTA so one tile's MMAs overlap the other's epilogue
     p->tiles_per_cta = 2;
     build_tiles(p->geom, p->tile_rows, p->tiles, 2);
@@ -848,10 +854,12 @@ static int do_rollout_score(simba_planner_t* p, const float* states, const float
   if (const char* tlp = getenv("SIMBA_TC_TIMELINE_PTR"))   // debug builds only (tools/tc_timeline.py)
     prm.traj_out = reinterpret_cast<float*>(strtoull(tlp, nullptr, 10));
   if (p->cfg.precision == SIMBA_PREC_BF16_TC) {
-    if (p->model->cfg.units == 128)
+    if (p->model->cfg.units <= 128) {
       CUDA_TRY(launch_rollout_tc(prm, prm.n_tiles, (cudaStream_t)stream));
-    else
+    } else {
+      prm.U = rollout_tc_wide_units(p->model->cfg.units);          // zero-padded width
       CUDA_TRY(launch_rollout_tc_wide(prm, prm.n_tiles, (cudaStream_t)stream));
+    }
   } else
     CUDA_TRY(launch_rollout_f32(prm, prm.n_tiles, (cudaStream_t)stream));
   return SIMBA_OK;

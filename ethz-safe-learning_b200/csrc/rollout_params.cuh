@@ -67,6 +67,7 @@ cudaError_t launch_rollout_tc(const RolloutParams& prm, int n_tiles, cudaStream_
 bool rollout_tc_supported(int O, int A, int L, int U, int H);
 cudaError_t launch_rollout_tc_wide(const RolloutParams& prm, int n_tiles, cudaStream_t stream);
 bool rollout_tc_wide_supported(int O, int A, int L, int U, int H);
-int64_t rollout_tc_wide_member_bytes(int L, int U);
+int rollout_tc_wide_units(int U);                  // U rounded up to a multiple of 16
+int64_t rollout_tc_wide_member_bytes(int L, int U);   // U = padded units
 
 }  // namespace simba

@@ -552,7 +552,8 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
 
 // ---- host side ------------------------------------------------------------------------------------
 bool rollout_tc_supported(int O, int A, int L, int U, int H) {
-  return U == kU && O >= 1 && O <= kMaxO && O + A <= 64 && A <= 4 && L >= 1 && L <= 6 && H >= 1 && H <= 64;
+  // narrower hidden layers run zero-padded to 128 units (simba_model_commit pads the images)
+  return U >= 1 && U <= kU && O >= 1 && O <= kMaxO && O + A <= 64 && A <= 4 && L >= 1 && L <= 6 && H >= 1 && H <= 64;
 }
 
 static size_t tc_smem_bytes(int L, int ntiles, int q, int nparts) {

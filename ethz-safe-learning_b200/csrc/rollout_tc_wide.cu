@@ -502,8 +502,11 @@ __global__ void __launch_bounds__(kWideThreads, 1) rollout_tc_wide_kernel(const 
 }
 
 // ---- host side ------------------------------------------------------------------------------------
+// widths that are not a multiple of 16 run zero-padded to the next one (rollout_tc_wide_units)
+int rollout_tc_wide_units(int U) { return (U + 15) / 16 * 16; }
+
 bool rollout_tc_wide_supported(int O, int A, int L, int U, int H) {
-  return U > 128 && U <= 440 && U % 16 == 0 && O >= 1 && O <= 60 && O + A + 2 <= 64 && A <= 4 &&
+  return U > 128 && rollout_tc_wide_units(U) <= 440 && O >= 1 && O <= 60 && O + A + 2 <= 64 && A <= 4 &&
          L >= 2 && L <= 6 && H >= 1 && H <= 64;
 }
 

@@ -21,7 +21,10 @@ torch = pytest.importorskip("torch")
 @pytest.mark.parametrize("cfg,over", [('tiny', {}), ('c1', {}), ('tiny', dict(S=1, N=700, P=8, E=2, K=10)),
                                       # wide models: the streaming tcgen05 kernel (rollout_tc_wide.cu)
                                       ('tiny', dict(U=400, L=2)), ('tiny', dict(U=256, L=3, N=100)),
-                                      ('tiny', dict(U=144, L=4)), ('c5', dict(H=10)), ('c5', {})])
+                                      ('tiny', dict(U=144, L=4)), ('c5', dict(H=10)), ('c5', {}),
+                                      # zero-padded widths: 64 / 72 -> 128 (rollout_tc.cu), 130 -> 144 and 200 -> 208 (wide)
+                                      ('tiny', dict(U=64)), ('tiny', dict(U=72, L=3)), ('tiny', dict(U=130, L=2)),
+                                      ('tiny', dict(U=200, L=3))])
 def test_tc_rollout_rows_close_to_oracle(cfg, over):
     from simba_b200 import _lib
     lib = _lib.load()
