@@ -675,7 +675,7 @@ extern "C" int simba_planner_create(simba_model_t* model, const simba_planner_co
       !rollout_tc_wide_supported(mc.obs_dim, mc.act_dim, mc.n_layers, mc.units, cfg->horizon))
     return fail(SIMBA_ERR_UNSUPPORTED,
                 "bf16 tcgen05 rollout covers units <= 128 (obs_dim <= 60, obs_dim+act_dim <= 64) and "
-                "wide models with 128 < units <= 440 (obs_dim+act_dim <= 62, 2..6 layers); "
+                "wide models with 128 < units <= 440 (obs_dim+act_dim <= 62, 1..6 layers); "
                 "use precision fp32 for this shape");
   int rc = validate_scorer(cfg->scorer, mc.obs_dim);
   if (rc != SIMBA_OK) return rc;

@@ -507,7 +507,7 @@ int rollout_tc_wide_units(int U) { return (U + 15) / 16 * 16; }
 
 bool rollout_tc_wide_supported(int O, int A, int L, int U, int H) {
   return U > 128 && rollout_tc_wide_units(U) <= 440 && O >= 1 && O <= 60 && O + A + 2 <= 64 && A <= 4 &&
-         L >= 2 && L <= 6 && H >= 1 && H <= 64;
+         L >= 1 && L <= 6 && H >= 1 && H <= 64;
 }
 
 int64_t rollout_tc_wide_member_bytes(int L, int U) {
