@@ -1,4 +1,12 @@
-"""clock64 timeline of one chain-kernel CTA (needs the -DSIMBA_TRAIN_TIMELINE build)."""
+"""clock64 timeline of one chain-kernel CTA of the trainer. Needs a side build of the library with the
+timeline stamps compiled in (the product build has none):
+
+    cd ethz-safe-learning_b200/csrc && make && \
+    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC \
+         -DSIMBA_TRAIN_TIMELINE -c trainer.cu -o /tmp/trainer_tl.o && \
+    nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../simba_b200/libsimba_b200_tl.so \
+         api.o cem_kernels.o rollout_f32.o rollout_tc.o rollout_tc_wide.o /tmp/trainer_tl.o -ldl
+"""
 import ctypes as C
 import os
 import subprocess
