@@ -30,6 +30,18 @@
 
 namespace simba {
 
+// Debug timeline (compile with -DSIMBA_TC_TIMELINE): epilogue thread 0 and the last epilogue warp's
+// lane 0 of CTA 0 stamp clock64() at phase boundaries into prm.traj_out (tools/tc_timeline.py c5).
+#ifdef SIMBA_TC_TIMELINE
+#define TLW(ev)                                                                                  \
+  do {                                                                                           \
+    if (tl_who >= 0 && blockIdx.x == 0)                                                          \
+      reinterpret_cast<long long*>(prm.traj_out)[(tl_who * 64 + tl_t) * 64 + (ev)] = clock64();  \
+  } while (0)
+#else
+#define TLW(ev) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kQ = 4;                         // epilogue threads per rollout row
@@ -43,10 +55,13 @@ constexpr int kTmemCols = 512;
 constexpr int OW = 64 / kQ;                   // head outputs / state dims / layer-0 K elements per thread
 constexpr int CW = 16;
 
+constexpr int kHeadGroup = 3;                 // head K-blocks (16 KB each) fetched per TMA tile
+
 struct WideShape {
   int U, KA, L;
   uint32_t hid_tile_bytes;      // [U x 64] bf16
-  uint32_t head_tile_bytes;     // [128 x 64] bf16
+  uint32_t head_tile_bytes;     // [128 x 64] bf16 (one K-block; kHeadGroup of them travel together)
+  int head_tiles;               // ceil(KA / kHeadGroup)
   int tiles_per_step;
 };
 
@@ -56,15 +71,27 @@ __host__ __device__ inline WideShape wide_shape(int U, int L) {
   s.KA = (U + 2 + 63) / 64;
   s.hid_tile_bytes = (uint32_t)U * 128u;
   s.head_tile_bytes = 128u * 128u;
-  s.tiles_per_step = 1 + (L - 1) * s.KA + s.KA;
+  s.head_tiles = (s.KA + kHeadGroup - 1) / kHeadGroup;
+  s.tiles_per_step = 1 + (L - 1) * s.KA + s.head_tiles;
   return s;
+}
+
+__host__ __device__ inline uint32_t wide_stage_bytes(const WideShape& s) {
+  const uint32_t head = (uint32_t)kHeadGroup * s.head_tile_bytes;
+  const uint32_t big = s.hid_tile_bytes > head ? s.hid_tile_bytes : head;
+  return (big + 1023u) & ~1023u;
 }
 
 // source offset / size of tile `i` of the per-step stream
 __device__ __forceinline__ void wide_tile(const WideShape& s, int i, uint32_t& off, uint32_t& bytes) {
   const int n_hid = 1 + (s.L - 1) * s.KA;
-  if (i < n_hid) { off = (uint32_t)i * s.hid_tile_bytes; bytes = s.hid_tile_bytes; }
-  else { off = (uint32_t)n_hid * s.hid_tile_bytes + (uint32_t)(i - n_hid) * s.head_tile_bytes; bytes = s.head_tile_bytes; }
+  if (i < n_hid) { off = (uint32_t)i * s.hid_tile_bytes; bytes = s.hid_tile_bytes; return; }
+  // the heads' K-blocks are small (16 KB), so kHeadGroup consecutive ones travel as one tile: with
+  // one block per tile the two-stage ring was latency-bound there (4.9 k cycles for 2.6 k of MMAs)
+  const int ht = i - n_hid;
+  const int blocks = min(kHeadGroup, s.KA - ht * kHeadGroup);
+  off = (uint32_t)n_hid * s.hid_tile_bytes + (uint32_t)(ht * kHeadGroup) * s.head_tile_bytes;
+  bytes = (uint32_t)blocks * s.head_tile_bytes;
 }
 
 struct TileInfoW {
@@ -86,7 +113,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) rollout_tc_wide_kernel(const 
   // ---- shared memory carve-up (base is 1024-aligned: required by SWIZZLE_128B) -------------------
   uint8_t* a_smem = smem_raw;                                              // [KA][128 x 64] bf16 SW128
   uint8_t* b_smem = a_smem + (size_t)KA * kAtomBytes;                      // [kStages][U x 64] bf16 SW128
-  const uint32_t stage_bytes = (ws.hid_tile_bytes + 1023u) & ~1023u;
+  const uint32_t stage_bytes = wide_stage_bytes(ws);
   float* scale_smem = reinterpret_cast<float*>(b_smem + (size_t)kStages * stage_bytes);   // [2][64]
   float* pen_smem = scale_smem + 128;                                      // [kParts][64]
   const int nparts = 1 + prm.scorer.n_constraints;
@@ -163,25 +190,40 @@ __global__ void __launch_bounds__(kWideThreads, 1) rollout_tc_wide_kernel(const 
             mbar_wait(bar_a, a_phase);                             // this layer's A tile is complete
             a_phase ^= 1;
             tc_fence_after();
-            const int kblocks = layer == 0 ? 1 : KA;
-            for (int kb = 0; kb < kblocks; ++kb, ++tile) {
-              const int s = tile % kStages;
-              mbar_wait(bar_full[s], (tile / kStages) & 1);
-              tc_fence_after();
-              const uint32_t b_base = smem_u32(b_smem + (size_t)s * stage_bytes);
+            if (layer < L) {
+              const int kblocks = layer == 0 ? 1 : KA;
+              for (int kb = 0; kb < kblocks; ++kb, ++tile) {
+                const int s = tile % kStages;
+                mbar_wait(bar_full[s], (tile / kStages) & 1);
+                tc_fence_after();
+                const uint32_t b_base = smem_u32(b_smem + (size_t)s * stage_bytes);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {                        // UMMA_K = 16 -> 32 bytes along K
-                const uint64_t a_desc = umma_desc_sw128(a_base + (uint32_t)kb * kAtomBytes + (uint32_t)k * 32);
-                const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-                if (layer < L) {
+                for (int k = 0; k < 4; ++k) {                      // UMMA_K = 16 -> 32 bytes along K
+                  const uint64_t a_desc = umma_desc_sw128(a_base + (uint32_t)kb * kAtomBytes + (uint32_t)k * 32);
+                  const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
                   umma_bf16(tmem_base, a_desc, umma_desc_sw128(b_base + (uint32_t)k * 32), idesc1, acc);
                   umma_bf16(tmem_base + (uint32_t)N1, a_desc,
                             umma_desc_sw128(b_base + (uint32_t)N1 * 128u + (uint32_t)k * 32), idesc2, acc);
-                } else {
-                  umma_bf16(tmem_base, a_desc, umma_desc_sw128(b_base + (uint32_t)k * 32), idesc_head, acc);
                 }
+                umma_commit(bar_empty[s]);                         // stage free once these MMAs retire
               }
-              umma_commit(bar_empty[s]);                           // stage free once these MMAs retire
+            } else {
+              for (int ht = 0; ht < ws.head_tiles; ++ht, ++tile) {
+                const int s = tile % kStages;
+                mbar_wait(bar_full[s], (tile / kStages) & 1);
+                tc_fence_after();
+                const uint32_t b_base = smem_u32(b_smem + (size_t)s * stage_bytes);
+                const int blocks = min(kHeadGroup, KA - ht * kHeadGroup);
+                for (int j = 0; j < blocks; ++j) {
+                  const int kb = ht * kHeadGroup + j;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base, umma_desc_sw128(a_base + (uint32_t)kb * kAtomBytes + (uint32_t)k * 32),
+                              umma_desc_sw128(b_base + (uint32_t)j * ws.head_tile_bytes + (uint32_t)k * 32),
+                              idesc_head, (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(bar_empty[s]);
+              }
             }
             umma_commit(bar_acc);                                  // accumulator of this layer ready
           }
@@ -415,14 +457,23 @@ __global__ void __launch_bounds__(kWideThreads, 1) rollout_tc_wide_kernel(const 
       publish_a();                                       // layer-0 input of step 0 (also orders the partials)
       if (cgp == 0) combine(rs.dist, rs.cost);
 
+#ifdef SIMBA_TC_TIMELINE
+      const int tl_who = (lane == 0) ? (wl == 0 ? 0 : (wl == 4 * kQ - 1 ? 1 : -1)) : -1;
+      int tl_t = 0;
+#endif
       const int n_chunks = U >> 3;                       // 16-byte chunks per hidden activation row
       const int my_c0 = cgp * (n_chunks / kQ) + min(cgp, n_chunks % kQ);
       const int my_c1 = my_c0 + n_chunks / kQ + (cgp < n_chunks % kQ ? 1 : 0);
       for (int t = 0; t < H; ++t) {
+#ifdef SIMBA_TC_TIMELINE
+        tl_t = t;
+#endif
+        TLW(0);
         prefetch_actions(t + 1);
         // ---- hidden layers: TMEM -> ReLU -> bf16 -> swizzled A tile (bias is in the accumulator) ----
         for (int l = 0; l < L; ++l) {
           wait_accumulator();
+          TLW(1 + l * 4);
           // this column group's contiguous run of 16-byte chunks, eight chunks (64 columns = two
           // 32-column TMEM loads) in flight at a time
           for (int c0 = my_c0; c0 < my_c1; c0 += 8) {
@@ -456,7 +507,9 @@ __global__ void __launch_bounds__(kWideThreads, 1) rollout_tc_wide_kernel(const 
                            pack_relu_bf16(__uint_as_float(w[6]), __uint_as_float(w[7])));
             }
           }
+          TLW(2 + l * 4);
           publish_a();
+          TLW(3 + l * 4);
           if (prm.sampling_propagation) {
 #pragma unroll
             for (int c = 0; c < OW / 8; ++c)
@@ -465,10 +518,13 @@ __global__ void __launch_bounds__(kWideThreads, 1) rollout_tc_wide_kernel(const 
         }
         // ---- Gaussian heads + state update + next input + partial minima ---------------------------
         wait_accumulator();
+        TLW(40);
         if (prm.sampling_propagation) state_pass(std::false_type{}, std::true_type{}, t + 1);
         else state_pass(std::false_type{}, std::false_type{}, t + 1);
+        TLW(41);
         if (t + 1 < H) publish_a();
         else named_bar_sync<kEpiThreads>(2);
+        TLW(42);
         if (cgp == 0) {
           float next_dist, next_cost;
           combine(next_dist, next_cost);
@@ -487,6 +543,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) rollout_tc_wide_kernel(const 
           rs.dist = next_dist;
           rs.cost = next_cost;
         }
+        TLW(43);
       }
       if (cgp == 0 && row_ok && prm.row_return != nullptr) {
         prm.row_return[id.out] = rs.cum;
@@ -518,7 +575,7 @@ int64_t rollout_tc_wide_member_bytes(int L, int U) {
 static size_t wide_smem_bytes(int L, int U, int nparts) {
   const WideShape ws = wide_shape(U, L);
   size_t b = (size_t)ws.KA * kAtomBytes;
-  b += (size_t)kStages * ((ws.hid_tile_bytes + 1023u) & ~1023u);
+  b += (size_t)kStages * wide_stage_bytes(ws);
   b += 128 * sizeof(float) + kParts * 64 * sizeof(float);
   b += (size_t)kQ * nparts * 128 * sizeof(float);
   b += 6 * sizeof(uint64_t) + 2 * sizeof(uint32_t) + sizeof(TileInfoW);

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Phase timeline of the tcgen05 rollout kernel (needs the -DSIMBA_TC_TIMELINE build:
-SIMBA_B200_LIB=.../libsimba_b200_tl.so python tools/tc_timeline.py [c1|c4])."""
+SIMBA_B200_LIB=.../libsimba_b200_tl.so python tools/tc_timeline.py [c1|c4|c5]; c5 = wide kernel)."""
 import ctypes as C
 import os
 import sys
@@ -13,7 +13,7 @@ from simba_b200 import _lib, synthetic  # noqa: E402
 
 wl = sys.argv[1] if len(sys.argv) > 1 else 'c1'
 over = dict(S=64) if wl == 'c4' else {}
-c = synthetic.make_workload('c4' if wl == 'c4' else 'c1', **over)
+c = synthetic.make_workload({'c4': 'c4', 'c5': 'c5'}.get(wl, 'c1'), **over)
 pol = synthetic.build_policy(c, 'penalty', precision='bf16', seed=1)
 lib = _lib.load()
 pl = pol._ensure_planner()
