@@ -344,6 +344,12 @@ def main():
         extras['error'] = repr(e)
     if extras:
         line['extras'] = extras
+    if 'c5' in extras and 'bf16_20state' in extras.get('c5', {}):
+        tfw = extras['c5']['bf16_20state']['tflops']
+        line['roofline_wide'] = {"kernel": "rollout_tc_wide_kernel", "workload": "configs[4] x 20 states per call",
+                                 "bound": "tensor", "achieved": tfw, "peak": peak_tf, "unit": "TFLOP/s",
+                                 "frac": tfw / peak_tf, "traffic": None,
+                                 "note": "plan-level: algorithmic flops of the call / CUDA-event time of the call"}
     if 'c4' in extras and 'tflops_per_gpu' in extras['c4']:
         # the same kernel at a shape that fills the GPU (BASELINE configs[3], 1024 states per call):
         # whole planning calls, so it includes the small CEM kernels (< 1 % of the time there)
@@ -380,11 +386,11 @@ def bench_plain(synthetic, torch, c, precision, states, flush, K):
 
 def bench_wide(synthetic, torch, flush):
     """BASELINE configs[4]: the wide 10 x (4 x 400) ensemble, horizon 50 — single-state plans on the
-    streaming tcgen05 kernel (bf16) and on the fp32 kernel, plus 5 states per call (150 row tiles = one
-    wave) for the kernel's throughput."""
+    streaming tcgen05 kernel (bf16) and on the fp32 kernel, plus 5 and 20 states per call (120 / 480
+    row tiles) for the kernel's throughput."""
     out = {}
     fpt = None
-    for precision, S in (('bf16', 1), ('fp32', 1), ('bf16', 5)):
+    for precision, S in (('bf16', 1), ('fp32', 1), ('bf16', 5), ('bf16', 20)):
         c = synthetic.make_workload('c5', S=S, seed=0)
         pol = synthetic.build_policy(c, 'penalty', precision=precision, seed=31)
         st = torch.from_numpy(synthetic.make_state(c['sensors'], seed=500, n_states=S).reshape(S, -1)).cuda()
