@@ -212,11 +212,17 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
         // The tile's A operand for `layer` is complete once every thread of the tile has passed the
         // named barrier below (each fenced its own writes to the async proxy first); the tile's
         // elected thread then issues that layer's MMAs and commits them onto the tile's mbarrier.
+#ifdef SIMBA_TC_TIMELINE
+        const int tl_who = (j == 0 && lane == 0) ? (wl == 0 ? 0 : (wl == 4 * Q - 1 ? 1 : -1)) : -1;
+        int tl_t = 0;
+#endif
         const bool issuer = (wl == 0) && (lane == 0);
         auto tile_sync_and_issue = [&](int layer) {
           tmem_st_wait();                                     // this thread's A-operand stores have landed
+          TL(48 + layer);
           tc_fence_before();
           named_bar_sync<kTileThreads>(2 + j);
+          TL(54 + layer);
           if (issuer) {
             tc_fence_after();
             const int ksteps = (layer == 0) ? 4 : 8;          // K = 64 or 128, UMMA_K = 16
@@ -464,10 +470,6 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
         // (the partials are next written after the tile has passed L more tile barriers, which the
         //  group-0 threads reading here reach only after combine())
 
-#ifdef SIMBA_TC_TIMELINE
-        const int tl_who = (j == 0 && lane == 0) ? (wl == 0 ? 0 : (wl == 4 * Q - 1 ? 1 : -1)) : -1;
-        int tl_t = 0;
-#endif
         for (int t = 0; t < H; ++t) {
 #ifdef SIMBA_TC_TIMELINE
           tl_t = t;

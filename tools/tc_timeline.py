@@ -42,5 +42,7 @@ for who, name in ((0, 'issuer (warp 0)'), (1, 'last warp of tile')):
             line.append("L%d wait->%5d epi->%5d sync+issue->%5d |" % (l, ev[1 + 4 * l] - base, ev[2 + 4 * l] - base, ev[3 + 4 * l] - base))
         line.append("head wait->%5d pass->%5d sync+issue->%5d score->%5d  total %5d" % (
             ev[40] - base, ev[41] - base, ev[42] - base, ev[43] - base, t[who, step + 1][0] - base))
+        line.append("| issue detail (st_wait, barrier) per layer: " + ' '.join(
+            "%d:(%d,%d)" % (l, ev[48 + l] - base, ev[54 + l] - base) for l in range(L + 1)))
         rows.append(' '.join(line))
     print('\n'.join(rows[:6]))
