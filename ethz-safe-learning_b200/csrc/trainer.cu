@@ -203,6 +203,11 @@ struct ChainArgs {
   int tiles_cap;
   int train;
   float* out_loss;
+  // Dropout after every hidden ReLU in training (mlp_ensemble.py:17-22): keep = u01(philox) >= rate,
+  // kept activations scaled by 1 / (1 - rate). Counter (column block, batch row, iteration,
+  // member | layer << 8 | stream 4 << 28), key = dropout_seed — restated in oracle/philox.py.
+  float dropout_rate, dropout_scale;
+  uint64_t dropout_seed;
 };
 
 struct ChunkCursor {      // walks the chunks of the chain in execution order
@@ -445,11 +450,27 @@ train_chain_kernel(ChainArgs a, OptParams opt, const FitDesc* desc, TrainState* 
               v[j + 1] = d_pre;
             }
           } else {
+            float keep[4] = {1.0f, 1.0f, 1.0f, 1.0f};          // forward: dropout mask / (1 - rate)
+            float back = 1.0f;                                   // backward: the same 1 / (1 - rate)
+            if (a.train && a.dropout_rate > 0.0f) {
+              if (p.kind == kPassHidden) {
+                const uint4 bits = philox4x32_10(
+                    make_uint4((uint32_t)(c0 >> 2), (uint32_t)r, (uint32_t)(st->iterations + step_off),
+                               (uint32_t)e | ((uint32_t)cur.pass << 8) | (4u << 28)),
+                    philox_key(a.dropout_seed));
+                keep[0] = u01(bits.x) >= a.dropout_rate ? a.dropout_scale : 0.0f;
+                keep[1] = u01(bits.y) >= a.dropout_rate ? a.dropout_scale : 0.0f;
+                keep[2] = u01(bits.z) >= a.dropout_rate ? a.dropout_scale : 0.0f;
+                keep[3] = u01(bits.w) >= a.dropout_rate ? a.dropout_scale : 0.0f;
+              } else {
+                back = a.dropout_scale;       // H > 0 <=> unit active AND kept (H is stored after dropout)
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const bool ok = c0 + j < p.n_dim;
-              if (p.kind == kPassHidden) v[j] = ok ? fmaxf(v[j] + pb[j], 0.0f) : 0.0f;
-              else v[j] = (ok && row_ok && pm[i][j] > 0.0f) ? v[j] : 0.0f;
+              if (p.kind == kPassHidden) v[j] = ok ? fmaxf(v[j] + pb[j], 0.0f) * keep[j] : 0.0f;
+              else v[j] = (ok && row_ok && pm[i][j] > 0.0f) ? v[j] * back : 0.0f;
             }
           }
           // columns past n_dim are written as zeros so that the next pass can consume k in groups of 4
@@ -796,6 +817,8 @@ extern "C" int simba_trainer_create(simba_model_t* model, const simba_trainer_co
   if (!(cfg->beta1 >= 0.0f && cfg->beta1 < 1.0f && cfg->beta2 >= 0.0f && cfg->beta2 < 1.0f) ||
       !(cfg->epsilon > 0.0f) || !(cfg->learning_rate >= 0.0f))
     return set_error(SIMBA_ERR_BAD_CONFIG, "Adam hyper-parameters out of range");
+  if (!(cfg->dropout_rate >= 0.0f && cfg->dropout_rate < 1.0f))
+    return set_error(SIMBA_ERR_BAD_CONFIG, "dropout_rate %g outside [0, 1)", cfg->dropout_rate);
   int rc = simba_device_check();
   if (rc) return rc;
   const simba_model_config_t* mc = model_config(model);
@@ -925,6 +948,9 @@ static int enqueue_chain(simba_trainer_t* t, const float* x, int64_t x_estride, 
   a.theta = t->theta; a.thetaT = t->thetaT; a.pn = t->pn; a.pnT = t->pnT;
   a.ld_act = t->ld_act; a.out_dim = t->O; a.ensemble = t->E; a.aligned = t->aligned;
   a.partial = t->partial; a.tiles_cap = t->tiles_cap; a.train = train; a.out_loss = out_loss;
+  a.dropout_rate = t->cfg.dropout_rate;
+  a.dropout_scale = 1.0f / (1.0f - t->cfg.dropout_rate);
+  a.dropout_seed = t->cfg.dropout_seed;
   // the smallest row tile that keeps the grid within about one wave of SMs
   const int TR = chain_tile_rows(t, grid_rows);
   dim3 grid((grid_rows + TR - 1) / TR, t->E);

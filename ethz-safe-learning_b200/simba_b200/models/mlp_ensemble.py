@@ -73,9 +73,10 @@ class MlpEnsemble(object):
         activation = mlp_params.get('activation', 'tf.nn.relu')
         if activation not in ('tf.nn.relu', 'relu'):
             raise _lib.SimbaError(-6, "only ReLU hidden activations are fused (got %r)" % (activation,))
-        # inference runs with training=False, so dropout is the identity there; the training
-        # kernels implement the shipped dropout_rate 0.0 (config/models.yaml:13) only
+        # inference runs with training=False, so dropout is the identity there; training_step applies
+        # it after every hidden ReLU (mlp_ensemble.py:17-22) with Philox masks keyed by dropout_seed
         self.dropout_rate = float(mlp_params.get('dropout_rate', 0.0))
+        self.dropout_seed = int(seed)
         rng = np.random.default_rng(seed)
         self.ensemble = []
         for e in range(ensemble_size):
@@ -212,14 +213,12 @@ class MlpEnsemble(object):
         self._trained_ahead = False
 
     def _ensure_trainer(self):
-        if self.dropout_rate != 0.0:
-            raise _lib.SimbaError(-6, "training with dropout_rate %g is not offered (shipped 0.0)"
-                                  % self.dropout_rate)
         h = self._ensure_handle()
         if self._trainer is None:
             cfg = _lib.TrainerConfig(int(self.batch_size), self.EVAL_ROWS, float(self.learning_rate),
                                      int(self.learning_rate_schedule), int(self.training_steps),
-                                     int(self.train_epochs), 0.9, 0.999, 1e-5, 1.0)
+                                     int(self.train_epochs), 0.9, 0.999, 1e-5, 1.0,
+                                     float(self.dropout_rate), int(self.dropout_seed))
             t = C.c_void_p()
             _lib.check(self._lib.simba_trainer_create(h, C.byref(cfg), C.byref(t)))
             self._trainer = t

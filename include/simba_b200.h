@@ -262,6 +262,8 @@ typedef struct simba_trainer_config {
   float beta1, beta2;        /* Keras defaults 0.9, 0.999                                       */
   float epsilon;             /* mlp_ensemble.py:117 (1e-5)                                      */
   float clipvalue;           /* mlp_ensemble.py:116 (1.0); <= 0 disables clipping               */
+  float dropout_rate;        /* models.yaml:13 (0.0): Dropout after every hidden ReLU in training */
+  uint64_t dropout_seed;     /* Philox key of the dropout masks (stream 4, see oracle/philox.py)  */
 } simba_trainer_config_t;
 
 /* Copies the model's current (set_layer) weights as fp32 master weights; Adam state zeroed. The

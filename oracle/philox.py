@@ -39,6 +39,7 @@ PHILOX_W1 = 0xBB67AE85
 STREAM_ACTION = 1
 STREAM_NOISE = 2
 STREAM_FINAL = 3
+STREAM_DROPOUT = 4      # training only: counter (column block, batch row, iteration, member | layer << 8 | 4 << 28)
 
 _MASK32 = np.uint64(0xFFFFFFFF)
 
@@ -132,3 +133,16 @@ def final_normals(seed, act_dim, state_index=0):
     """nu for cem_mpc.py:68 — shape [act_dim]."""
     return _normals(seed, act_dim, np.uint32(0), np.uint32(0),
                     np.uint32(state_index | (STREAM_FINAL << 28)))
+
+
+def dropout_keep(seed, iteration, member, layer, rows, units, rate):
+    """Dropout keep mask of the trainer (csrc/trainer.cu): [rows, units] bool, keep = u >= rate with
+    u = uniform_from_bits(philox(column block j, batch row r, iteration, member | layer << 8 | 4 << 28))."""
+    nblk = (units + 3) // 4
+    ctr = np.empty((rows, nblk, 4), dtype=np.uint32)
+    ctr[..., 0] = np.arange(nblk, dtype=np.uint32)[None, :]
+    ctr[..., 1] = np.arange(rows, dtype=np.uint32)[:, None]
+    ctr[..., 2] = np.uint32(iteration)
+    ctr[..., 3] = np.uint32(member | (layer << 8) | (STREAM_DROPOUT << 28))
+    u = uniform_from_bits(philox4x32(ctr, _key(seed)))
+    return (u >= np.float32(rate)).reshape(rows, nblk * 4)[:, :units]

@@ -8,9 +8,11 @@ pinned by calculus instead: tests/test_train_oracle.py checks every analytic gra
 float64 central differences and the Adam update against a hand-computed step.
 
 Restated pieces (file:line of what each follows):
-  * forward, training=True with dropout_rate 0.0 (config/models.yaml:13) == inference forward:
-    h_l = relu(h_{l-1} W_l + b_l) (mlp_ensemble.py:17-22); mu = h_L W_mu + b_mu;
-    var = softplus(h_L W_v + b_v) + 1e-4 (mlp_ensemble.py:28-34)
+  * forward: h_l = dropout(relu(h_{l-1} W_l + b_l)) (mlp_ensemble.py:17-22); mu = h_L W_mu + b_mu;
+    var = softplus(h_L W_v + b_v) + 1e-4 (mlp_ensemble.py:28-34). Dropout (training only, shipped rate
+    0.0, config/models.yaml:13) is tf.nn.dropout: x * keep / (1 - rate); the keep masks are inputs of
+    the oracle (TensorFlow's generator cannot be reproduced), produced by oracle/philox.dropout_keep
+    when the device trainer's masks are to be matched
   * negative_log_likelihood (mlp_ensemble.py:64-67):
     0.5 * mean(log(2 pi var)) + 0.5 * mean((mu - y)^2 / var), means over batch x outputs
   * loss = sum_e nll_e / E (mlp_ensemble.py:139-141)
@@ -53,22 +55,26 @@ class MemberNet:
         self.arrays = [np.array(a, dtype=self.dtype) for a in arrays]
         self.n_layers = len(arrays) // 2 - 2
 
-    def forward(self, x):
-        """Returns (mu, var, cache) — cache holds what backward needs."""
+    def forward(self, x, keep=None):
+        """Returns (mu, var, cache) — cache holds what backward needs. keep: per hidden layer the
+        dropout multiplier [B, U] (0 or 1 / (1 - rate)), or None (no dropout)."""
         L = self.n_layers
         hs = [np.asarray(x, dtype=self.dtype)]
         for l in range(L):
-            hs.append(np.maximum(hs[-1] @ self.arrays[2 * l] + self.arrays[2 * l + 1], 0))
+            h = np.maximum(hs[-1] @ self.arrays[2 * l] + self.arrays[2 * l + 1], 0)
+            if keep is not None:
+                h = h * keep[l].astype(self.dtype)
+            hs.append(h)
         mu = hs[-1] @ self.arrays[2 * L] + self.arrays[2 * L + 1]
         raw = hs[-1] @ self.arrays[2 * L + 2] + self.arrays[2 * L + 3]
         var = tf_softplus(raw) + self.dtype.type(1e-4)
         return mu, var, (hs, raw)
 
-    def loss_and_grads(self, x, y, loss_scale=1.0):
+    def loss_and_grads(self, x, y, loss_scale=1.0, keep=None):
         """d(loss_scale * nll)/d(variables), in Keras variable order."""
         dt = self.dtype.type
         L = self.n_layers
-        mu, var, (hs, raw) = self.forward(x)
+        mu, var, (hs, raw) = self.forward(x, keep)
         y = np.asarray(y, dtype=self.dtype)
         loss = negative_log_likelihood(y, mu, var) * dt(loss_scale)
         c = dt(loss_scale) / dt(mu.size)
@@ -85,7 +91,8 @@ class MemberNet:
         grads[2 * L + 3] = d_raw.sum(axis=0)
         d_h = d_mu @ self.arrays[2 * L].T + d_raw @ self.arrays[2 * L + 2].T
         for l in range(L - 1, -1, -1):
-            d_z = d_h * (hs[l + 1] > 0)
+            # relu'(z) and the dropout multiplier: hs[l + 1] > 0 <=> active and kept
+            d_z = d_h * (hs[l + 1] > 0) * (keep[l].astype(self.dtype) if keep is not None else dt(1.0))
             grads[2 * l] = hs[l].T @ d_z
             grads[2 * l + 1] = d_z.sum(axis=0)
             if l > 0:
@@ -126,7 +133,8 @@ class EnsembleTrainer:
     """training_step / validation_step / fit of mlp_ensemble.py:134-187 on numpy arrays."""
 
     def __init__(self, members, batch_size=64, learning_rate=0.00025, learning_rate_schedule=True,
-                 training_steps=5000, train_epochs=1, dtype=np.float32):
+                 training_steps=5000, train_epochs=1, dtype=np.float32, dropout_rate=0.0, dropout_seed=0):
+        self.dropout_rate, self.dropout_seed = float(dropout_rate), int(dropout_seed)
         self.nets = [MemberNet(m, dtype) for m in members]
         self.batch_size = batch_size
         self.training_steps = training_steps
@@ -145,7 +153,15 @@ class EnsembleTrainer:
         loss = self.nets[0].dtype.type(0.0)
         grads = []
         for e, net in enumerate(self.nets):
-            l, g = net.loss_and_grads(inputs[e], targets[e], 1.0 / E)
+            keep = None
+            if self.dropout_rate > 0.0:
+                from . import philox
+                scale = np.float32(1.0) / (np.float32(1.0) - np.float32(self.dropout_rate))
+                keep = [philox.dropout_keep(self.dropout_seed, self.optimizer.iterations, e, l,
+                                            inputs[e].shape[0], net.arrays[2 * l].shape[1],
+                                            self.dropout_rate).astype(np.float32) * scale
+                        for l in range(net.n_layers)]
+            l, g = net.loss_and_grads(inputs[e], targets[e], 1.0 / E, keep)
             loss = loss + l
             grads += g
         self.last_grads = grads

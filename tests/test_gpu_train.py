@@ -200,3 +200,35 @@ def test_training_step_random_shapes(n_out, n_act, E, B, rows_frac, L, U, steps,
         for g, r in zip(ens.trainer_arrays('weights', e), ora.nets[e].arrays):
             np.testing.assert_allclose(g, r, rtol=0, atol=4e-3 * steps)
     assert ens.iterations == steps
+
+
+@pytest.mark.parametrize('shape,rate', [((62, 60, 3, 64, 4, 128), 0.1), ((12, 10, 2, 16, 2, 40), 0.5),
+                                        ((20, 18, 2, 24, 3, 200), 0.25)])
+def test_dropout_training_steps_match_oracle(shape, rate):
+    """dropout_rate > 0 (mlp_ensemble.py:17-22, training=True): the device draws the keep masks from
+    Philox stream 4; the oracle is fed oracle/philox.dropout_keep's restatement of the same counters.
+    Loss and weights over three steps within the training tolerance; validation_step (training=False)
+    is unaffected by the rate."""
+    n_in, n_out, E, B, L, U = shape
+    ens = MlpEnsemble(n_in, n_out, E, batch_size=B, learning_rate=1e-3, learning_rate_schedule=False,
+                      mlp_params=dict(n_layers=L, units=U, dropout_rate=rate), seed=7)
+    ora = T.EnsembleTrainer([m.get_weights() for m in ens.ensemble], batch_size=B, learning_rate=1e-3,
+                            learning_rate_schedule=False, dropout_rate=rate, dropout_seed=7)
+    rng = np.random.default_rng(12)
+    x, y = _data(rng, E, B, n_in, n_out)
+    plain = _ensemble(n_in, n_out, E, B, L, U, seed=7)
+    assert float(ens.validation_step(x[0], y[0])) == pytest.approx(float(plain.validation_step(x[0], y[0])), rel=1e-6)
+    first = None
+    for s in range(3):
+        x, y = _data(rng, E, B, n_in, n_out)
+        got, want = float(ens.training_step(x, y)), float(ora.training_step(x, y))
+        assert got == pytest.approx(want, rel=2e-4, abs=1e-6), s
+        first = got if first is None else first
+    n_var = 2 * L + 4
+    for e in range(E):
+        for g, r in zip(ens.trainer_arrays('grads', e), ora.last_grads[e * n_var:(e + 1) * n_var]):
+            np.testing.assert_allclose(g, r, rtol=2e-3, atol=2e-6)
+        for g, r in zip(ens.trainer_arrays('weights', e), ora.nets[e].arrays):
+            np.testing.assert_allclose(g, r, rtol=0, atol=1.2e-2)
+    # dropout changes the step: the same data without dropout gives a different loss
+    assert abs(float(plain.training_step(x, y)) - first) > 1e-4

@@ -95,3 +95,30 @@ def test_training_reduces_loss_and_batches_cover_rows():
 def test_uneven_batches_follow_array_split():
     idx = T.make_batch_index(np.random.default_rng(2), 10, 2, 4, 3)     # ceil(10/4) = 3 batches
     assert [b.shape[1] for b in idx] == [4, 3, 3]
+
+
+def test_dropout_gradients_and_mask_statistics():
+    """Dropout (training only): gradients with a given keep mask against central differences, and the
+    Philox mask contract keeps a fraction 1 - rate of the units, independently per (member, layer, step)."""
+    from oracle import philox
+    rng = np.random.default_rng(3)
+    net = T.MemberNet(_member(rng, 5, 3, 8, 2, np.float64), np.float64)
+    x, y = rng.normal(size=(7, 5)), rng.normal(size=(7, 3))
+    keep = [philox.dropout_keep(1, 0, 0, l, 7, 8, 0.3).astype(np.float64) / 0.7 for l in range(2)]
+    loss, grads = net.loss_and_grads(x, y, 1.0, keep)
+    h = 1e-6
+    for a, g in zip(net.arrays, grads):
+        flat = a.reshape(-1)
+        for j in rng.choice(flat.size, size=min(flat.size, 5), replace=False):
+            old = flat[j]
+            flat[j] = old + h
+            up = T.negative_log_likelihood(y, *net.forward(x, keep)[:2])
+            flat[j] = old - h
+            dn = T.negative_log_likelihood(y, *net.forward(x, keep)[:2])
+            flat[j] = old
+            assert g.reshape(-1)[j] == pytest.approx((up - dn) / (2 * h), rel=2e-5, abs=1e-9)
+    m = philox.dropout_keep(9, 3, 1, 2, 256, 400, 0.25)
+    assert m.shape == (256, 400) and abs(m.mean() - 0.75) < 0.01
+    assert not np.array_equal(m, philox.dropout_keep(9, 4, 1, 2, 256, 400, 0.25))      # new mask every step
+    assert not np.array_equal(m, philox.dropout_keep(9, 3, 0, 2, 256, 400, 0.25))      # and per member
+    assert np.array_equal(philox.dropout_keep(9, 3, 1, 2, 256, 400, 0.0), np.ones((256, 400), bool))
