@@ -95,7 +95,11 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
   float* pen_smem = scale_smem + 128;                                      // [kParts][64]: 0 in slice, +inf outside
   const int nparts = 1 + prm.scorer.n_constraints;                         // goal + constrained lidars
   float* part_smem = pen_smem + kParts * 64;                               // [NTILES][Q][nparts][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(part_smem + NTILES * Q * nparts * 128);
+  // N(0,1) draws of the current step, packed bf16x2, [OW / 2][threads] (thread-minor: conflict-free).
+  // They are produced during the hidden layers and consumed by the head pass; parking them here
+  // instead of in OW registers leaves the head pass room to keep more TMEM loads in flight.
+  uint32_t* noise_smem = reinterpret_cast<uint32_t*>(part_smem + NTILES * Q * nparts * 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(noise_smem + (OW / 2) * kEpiThreads);
   // bars[0] = weights landed; bars[1 + j] = accumulator ready (tile j)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * NTILES);
   TileInfo* tinfo = reinterpret_cast<TileInfo*>(tmem_slot + 2);
@@ -285,9 +289,9 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
         // (seed, iteration, t, row, o), not on the network, so they are produced one Philox block
         // (8 normals) at a time right after this tile's MMAs have been issued for a hidden layer,
         // i.e. in the shadow of the tensor-core latency instead of inside the head epilogue.
-        float e_pre[OW];
+        uint32_t* my_noise = noise_smem + threadIdx.x;      // element pair i at my_noise[i * kEpiThreads]
 #pragma unroll
-        for (int i = 0; i < OW; ++i) e_pre[i] = 0.0f;
+        for (int i = 0; i < OW / 2; ++i) my_noise[i * kEpiThreads] = 0u;
         auto make_noise = [&](int call, int t) {              // call in [0, OW / 8)
 #pragma unroll
           for (int c = 0; c < OW / 8; ++c) {
@@ -297,7 +301,9 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
             if (prm.eps != nullptr) {
               const float* ep = prm.eps + (((int64_t)id.s * H + t) * ((int64_t)g.P * g.N) + id.r_global) * O;
 #pragma unroll
-              for (int q = 0; q < 8; ++q) e_pre[c * 8 + q] = (o0 + q < O) ? ep[o0 + q] : 0.0f;
+              for (int q = 0; q < 8; q += 2)
+                my_noise[(c * 4 + q / 2) * kEpiThreads] =
+                    pack_bf16((o0 + q < O) ? ep[o0 + q] : 0.0f, (o0 + q + 1 < O) ? ep[o0 + q + 1] : 0.0f);
             } else {
               float z[8];
 #ifdef ABL_NO_PHILOX
@@ -308,7 +314,7 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
                                   (uint32_t)id.r_global, (uint32_t)(o0 >> 3), z);
 #endif
 #pragma unroll
-              for (int q = 0; q < 8; ++q) e_pre[c * 8 + q] = z[q];
+              for (int q = 0; q < 8; q += 2) my_noise[(c * 4 + q / 2) * kEpiThreads] = pack_bf16(z[q], z[q + 1]);
             }
           }
         };
@@ -346,14 +352,21 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
 #pragma unroll
                 for (int q = 0; q < 8; ++q) d[q] = __uint_as_float(vm[jb * 8 + q]);
                 if (kSample && o0 < O) {
+                  float eps8[8];
+#pragma unroll
+                  for (int q = 0; q < 8; q += 2) {
+                    const uint32_t pk = my_noise[((sub * CW + jb * 8 + q) / 2) * kEpiThreads];
+                    eps8[q] = __uint_as_float(pk << 16);             // bf16 -> fp32: low half first
+                    eps8[q + 1] = __uint_as_float(pk & 0xffff0000u);
+                  }
 #pragma unroll
                   for (int q = 0; q < 8; ++q) {
 #ifdef ABL_NO_SOFTPLUS
                     const float var = __uint_as_float(vv[jb * 8 + q]) * 1e-6f + 3e-4f;
-                    d[q] = fmaf(var, e_pre[sub * CW + jb * 8 + q], d[q]);
+                    d[q] = fmaf(var, eps8[q], d[q]);
 #else
                     const float var = softplus_fast(__uint_as_float(vv[jb * 8 + q])) + 1e-4f;
-                    d[q] = fmaf(sqrt_approx(var), e_pre[sub * CW + jb * 8 + q], d[q]);
+                    d[q] = fmaf(sqrt_approx(var), eps8[q], d[q]);
 #endif
                   }
                 }
@@ -564,6 +577,7 @@ static size_t tc_smem_bytes(int L, int ntiles, int q, int nparts) {
   b += 128 * sizeof(float);                                        // scaler
   b += kParts * 64 * sizeof(float);                                // slice penalty table
   b += (size_t)ntiles * q * nparts * 128 * sizeof(float);          // partial minima exchange
+  b += (size_t)(64 / q / 2) * (ntiles * q * 128) * sizeof(uint32_t);   // bf16x2 noise of the current step
   b += (1 + 2 * ntiles) * sizeof(uint64_t) + 2 * sizeof(uint32_t) + ntiles * sizeof(TileInfo);
   return b + 1024;                                                 // alignment slack
 }
