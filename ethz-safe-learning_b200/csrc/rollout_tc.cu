@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
           float cmin[SIMBA_MAX_CONSTRAINTS];
 #pragma unroll
           for (int q = 0; q < SIMBA_MAX_CONSTRAINTS; ++q) cmin[q] = INFINITY;
-#pragma unroll
+#pragma unroll 1
           for (int sub = 0; sub < NSUB; ++sub) {
             const int oc = o_base + sub * CW;               // first state dim of this chunk
             const bool full = oc + CW <= O;                 // warp-uniform: no padding / action columns
