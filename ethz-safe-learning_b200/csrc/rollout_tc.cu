@@ -99,7 +99,10 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
   // They are produced during the hidden layers and consumed by the head pass; parking them here
   // instead of in OW registers leaves the head pass room to keep more TMEM loads in flight.
   uint32_t* noise_smem = reinterpret_cast<uint32_t*>(part_smem + NTILES * Q * nparts * 128);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(noise_smem + (OW / 2) * kEpiThreads);
+  // running objective of every rollout row (RowScore fields, field-major): only one of the Q threads of a
+  // row scores, and only once per step, so the seven words live here instead of in registers
+  uint32_t* rs_smem = noise_smem + (OW / 2) * kEpiThreads;                 // [8][NTILES * 128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rs_smem + 8 * NTILES * 128);
   // bars[0] = weights landed; bars[1 + j] = accumulator ready (tile j)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * NTILES);
   TileInfo* tinfo = reinterpret_cast<TileInfo*>(tmem_slot + 2);
@@ -473,13 +476,20 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
           cost = sc.constrain_indicator ? (cst > 0.0f ? 1.0f : 0.0f) : cst;
         };
 
-        RowScore rs;
-        rs.cum = 0.0f; rs.costsum = 0.0f; rs.cmask = 0ull; rs.done = false; rs.dist = 0.0f; rs.cost = 0.0f;
+        constexpr int kRsStride = NTILES * 128;
+        uint32_t* my_rs = rs_smem + j * 128 + r;            // cum, costsum, cmask lo / hi, dist, cost, done
         prefetch_actions(0);
         state_pass(std::true_type{}, std::false_type{}, 0, 0);
         if (issuer) mbar_wait(bar_w, 0);                 // weights have landed before the first MMA
         tile_sync_and_issue(0);                          // also orders the partials for combine()
-        if (cgp == 0) combine(rs.dist, rs.cost);
+        if (cgp == 0) {
+          float d0, c0;
+          combine(d0, c0);
+          my_rs[0] = 0u; my_rs[kRsStride] = 0u; my_rs[2 * kRsStride] = 0u; my_rs[3 * kRsStride] = 0u;
+          my_rs[4 * kRsStride] = __float_as_uint(d0);
+          my_rs[5 * kRsStride] = __float_as_uint(c0);
+          my_rs[6 * kRsStride] = 0u;
+        }
         // (the partials are next written after the tile has passed L more tile barriers, which the
         //  group-0 threads reading here reach only after combine())
 
@@ -534,6 +544,13 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
           if (cgp == 0) {
             float next_dist, next_cost;
             combine(next_dist, next_cost);
+            RowScore rs;
+            rs.cum = __uint_as_float(my_rs[0]);
+            rs.costsum = __uint_as_float(my_rs[kRsStride]);
+            rs.cmask = (uint64_t)my_rs[2 * kRsStride] | ((uint64_t)my_rs[3 * kRsStride] << 32);
+            rs.dist = __uint_as_float(my_rs[4 * kRsStride]);
+            rs.cost = __uint_as_float(my_rs[5 * kRsStride]);
+            rs.done = my_rs[6 * kRsStride] != 0u;
             const bool goal = rs.dist <= sc.goal_threshold;
             const float rew = step_reward(sc, rs.dist, next_dist, goal);
             if (done_first) {                                  // safe_cem_mpc.py:87-93
@@ -546,15 +563,20 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
               rs.done = rs.done || goal;
             }
             rs.costsum += rs.cost;
-            rs.dist = next_dist;
-            rs.cost = next_cost;
+            my_rs[0] = __float_as_uint(rs.cum);
+            my_rs[kRsStride] = __float_as_uint(rs.costsum);
+            my_rs[2 * kRsStride] = (uint32_t)rs.cmask;
+            my_rs[3 * kRsStride] = (uint32_t)(rs.cmask >> 32);
+            my_rs[4 * kRsStride] = __float_as_uint(next_dist);
+            my_rs[5 * kRsStride] = __float_as_uint(next_cost);
+            my_rs[6 * kRsStride] = rs.done ? 1u : 0u;
           }
           TL(43);
         }
         if (cgp == 0 && row_ok && prm.row_return != nullptr) {
-          prm.row_return[id.out] = rs.cum;
-          prm.row_costmask[id.out] = rs.cmask;
-          prm.row_costsum[id.out] = rs.costsum;
+          prm.row_return[id.out] = __uint_as_float(my_rs[0]);
+          prm.row_costmask[id.out] = (uint64_t)my_rs[2 * kRsStride] | ((uint64_t)my_rs[3 * kRsStride] << 32);
+          prm.row_costsum[id.out] = __uint_as_float(my_rs[kRsStride]);
         }
       }
     }
@@ -578,6 +600,7 @@ static size_t tc_smem_bytes(int L, int ntiles, int q, int nparts) {
   b += kParts * 64 * sizeof(float);                                // slice penalty table
   b += (size_t)ntiles * q * nparts * 128 * sizeof(float);          // partial minima exchange
   b += (size_t)(64 / q / 2) * (ntiles * q * 128) * sizeof(uint32_t);   // bf16x2 noise of the current step
+  b += (size_t)8 * ntiles * 128 * sizeof(uint32_t);                    // per-row running objective
   b += (1 + 2 * ntiles) * sizeof(uint64_t) + 2 * sizeof(uint32_t) + ntiles * sizeof(TileInfo);
   return b + 1024;                                                 // alignment slack
 }
