@@ -118,7 +118,9 @@ __global__ void __launch_bounds__(kWideThreads, 1) rollout_tc_wide_kernel(const 
   float* pen_smem = scale_smem + 128;                                      // [kParts][64]
   const int nparts = 1 + prm.scorer.n_constraints;
   float* part_smem = pen_smem + kParts * 64;                               // [kQ][nparts][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(part_smem + kQ * nparts * 128);
+  // running objective of every rollout row (RowScore fields, field-major), see rollout_tc.cu
+  uint32_t* rs_smem = reinterpret_cast<uint32_t*>(part_smem + kQ * nparts * 128);   // [8][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rs_smem + 8 * 128);
   // bars: [0,1] full, [2,3] empty, [4] A ready, [5] accumulator ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
   TileInfoW* tinfo = reinterpret_cast<TileInfoW*>(tmem_slot + 2);
@@ -450,12 +452,18 @@ __global__ void __launch_bounds__(kWideThreads, 1) rollout_tc_wide_kernel(const 
         cost = sc.constrain_indicator ? (cst > 0.0f ? 1.0f : 0.0f) : cst;
       };
 
-      RowScore rs;
-      rs.cum = 0.0f; rs.costsum = 0.0f; rs.cmask = 0ull; rs.done = false; rs.dist = 0.0f; rs.cost = 0.0f;
+      uint32_t* my_rs = rs_smem + r;                      // cum, costsum, cmask lo / hi, dist, cost, done
       prefetch_actions(0);
       state_pass(std::true_type{}, std::false_type{}, 0);
       publish_a();                                       // layer-0 input of step 0 (also orders the partials)
-      if (cgp == 0) combine(rs.dist, rs.cost);
+      if (cgp == 0) {
+        float d0, c0;
+        combine(d0, c0);
+        my_rs[0] = 0u; my_rs[128] = 0u; my_rs[256] = 0u; my_rs[384] = 0u;
+        my_rs[512] = __float_as_uint(d0);
+        my_rs[640] = __float_as_uint(c0);
+        my_rs[768] = 0u;
+      }
 
 #ifdef SIMBA_TC_TIMELINE
       const int tl_who = (lane == 0) ? (wl == 0 ? 0 : (wl == 4 * kQ - 1 ? 1 : -1)) : -1;
@@ -528,6 +536,13 @@ __global__ void __launch_bounds__(kWideThreads, 1) rollout_tc_wide_kernel(const 
         if (cgp == 0) {
           float next_dist, next_cost;
           combine(next_dist, next_cost);
+          RowScore rs;
+          rs.cum = __uint_as_float(my_rs[0]);
+          rs.costsum = __uint_as_float(my_rs[128]);
+          rs.cmask = (uint64_t)my_rs[256] | ((uint64_t)my_rs[384] << 32);
+          rs.dist = __uint_as_float(my_rs[512]);
+          rs.cost = __uint_as_float(my_rs[640]);
+          rs.done = my_rs[768] != 0u;
           const bool goal = rs.dist <= sc.goal_threshold;
           const float rew = step_reward(sc, rs.dist, next_dist, goal);
           if (done_first) {                                  // safe_cem_mpc.py:87-93
@@ -540,15 +555,20 @@ __global__ void __launch_bounds__(kWideThreads, 1) rollout_tc_wide_kernel(const 
             rs.done = rs.done || goal;
           }
           rs.costsum += rs.cost;
-          rs.dist = next_dist;
-          rs.cost = next_cost;
+          my_rs[0] = __float_as_uint(rs.cum);
+          my_rs[128] = __float_as_uint(rs.costsum);
+          my_rs[256] = (uint32_t)rs.cmask;
+          my_rs[384] = (uint32_t)(rs.cmask >> 32);
+          my_rs[512] = __float_as_uint(next_dist);
+          my_rs[640] = __float_as_uint(next_cost);
+          my_rs[768] = rs.done ? 1u : 0u;
         }
         TLW(43);
       }
       if (cgp == 0 && row_ok && prm.row_return != nullptr) {
-        prm.row_return[id.out] = rs.cum;
-        prm.row_costmask[id.out] = rs.cmask;
-        prm.row_costsum[id.out] = rs.costsum;
+        prm.row_return[id.out] = __uint_as_float(my_rs[0]);
+        prm.row_costmask[id.out] = (uint64_t)my_rs[256] | ((uint64_t)my_rs[384] << 32);
+        prm.row_costsum[id.out] = __uint_as_float(my_rs[128]);
       }
     }
   }
@@ -578,6 +598,7 @@ static size_t wide_smem_bytes(int L, int U, int nparts) {
   b += (size_t)kStages * wide_stage_bytes(ws);
   b += 128 * sizeof(float) + kParts * 64 * sizeof(float);
   b += (size_t)kQ * nparts * 128 * sizeof(float);
+  b += (size_t)8 * 128 * sizeof(uint32_t);                          // per-row running objective
   b += 6 * sizeof(uint64_t) + 2 * sizeof(uint32_t) + sizeof(TileInfoW);
   return b + 1024;                                                 // alignment slack
 }
