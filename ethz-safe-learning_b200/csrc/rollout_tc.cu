@@ -79,6 +79,11 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
   // hold the bf16 A operand (128 K-elements, two per 32-bit column). Layout:
   // [NTILES x 128 acc][NTILES x 64 state][NTILES x 64 A]  ->  256 / 512 columns (power of two)
   constexpr int kTmemCols = NTILES * 256;
+  // Throughput variant (two tiles, 512 threads at the 128-register cap): the step's noise, the
+  // per-row running objective and the Philox key are parked in shared memory to free registers.
+  // Latency variant (one tile): they stay in registers — no spills there, and the extra shared
+  // memory round trips would sit on the critical path.
+  constexpr bool kPark = NTILES > 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const RowGeom& g = prm.g;
   const int L = prm.L;
@@ -123,6 +128,8 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
   // everything above is independent of the previous kernel (the CEM update that wrote the actions
   // and the active flags); from here on its results are needed
   pdl_wait_prior_grid();
+  __shared__ uint64_t seed_sh;          // Philox key (kPark: read where it is used, not held in two registers)
+  if (threadIdx.x == 0) seed_sh = prm.seed_ptr ? *prm.seed_ptr : prm.seed;
   if (threadIdx.x < NTILES) {
     const int ti = blockIdx.x * NTILES + threadIdx.x;
     TileInfo info{0, 0, 0, 0};
@@ -200,7 +207,6 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
       if (ti.valid) {
         const bool row_ok = r < ti.count;
         const RowId id = decode_row(g, ti.member, ti.k0 + (row_ok ? r : 0));
-        const uint64_t seed = prm.seed_ptr ? *prm.seed_ptr : prm.seed;
         const uint32_t t_lane = tmem_base + ((uint32_t)((wl & 3) * 32) << 16) + (uint32_t)j * 128;
         const float* act_ptr = prm.actions + ((int64_t)id.s * g.N + id.i_global) * prm.action_stride;
         const bool done_first = objective_done_first(prm.objective);
@@ -293,8 +299,24 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
         // (8 normals) at a time right after this tile's MMAs have been issued for a hidden layer,
         // i.e. in the shadow of the tensor-core latency instead of inside the head epilogue.
         uint32_t* my_noise = noise_smem + threadIdx.x;      // element pair i at my_noise[i * kEpiThreads]
+        float e_pre[kPark ? 1 : OW];                        // the same draws in registers (latency variant)
+        const uint64_t seed_reg = kPark ? 0ull : (prm.seed_ptr ? *prm.seed_ptr : prm.seed);
+        if constexpr (kPark) {
 #pragma unroll
-        for (int i = 0; i < OW / 2; ++i) my_noise[i * kEpiThreads] = 0u;
+          for (int i = 0; i < OW / 2; ++i) my_noise[i * kEpiThreads] = 0u;
+        } else {
+#pragma unroll
+          for (int i = 0; i < OW; ++i) e_pre[i] = 0.0f;
+        }
+        auto put_noise = [&](int idx, float a, float b) {   // elements idx, idx + 1 (idx even)
+          const uint32_t pk = pack_bf16(a, b);             // both variants use the bf16-rounded draws,
+          if constexpr (kPark) {                               // so their rows stay bit-identical
+            my_noise[(idx / 2) * kEpiThreads] = pk;
+          } else {
+            e_pre[idx] = __uint_as_float(pk << 16);
+            e_pre[idx + 1] = __uint_as_float(pk & 0xffff0000u);
+          }
+        };
         auto make_noise = [&](int call, int t) {              // call in [0, OW / 8)
 #pragma unroll
           for (int c = 0; c < OW / 8; ++c) {
@@ -305,19 +327,18 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
               const float* ep = prm.eps + (((int64_t)id.s * H + t) * ((int64_t)g.P * g.N) + id.r_global) * O;
 #pragma unroll
               for (int q = 0; q < 8; q += 2)
-                my_noise[(c * 4 + q / 2) * kEpiThreads] =
-                    pack_bf16((o0 + q < O) ? ep[o0 + q] : 0.0f, (o0 + q + 1 < O) ? ep[o0 + q + 1] : 0.0f);
+                put_noise(c * 8 + q, (o0 + q < O) ? ep[o0 + q] : 0.0f, (o0 + q + 1 < O) ? ep[o0 + q + 1] : 0.0f);
             } else {
               float z[8];
 #ifdef ABL_NO_PHILOX
 #pragma unroll
               for (int q = 0; q < 8; ++q) z[q] = 0.3f + 0.01f * (float)(q + t);
 #else
-              philox_noise8<true>(seed, (uint32_t)id.s, (uint32_t)prm.iteration, (uint32_t)t,
+              philox_noise8<true>(kPark ? seed_sh : seed_reg, (uint32_t)id.s, (uint32_t)prm.iteration, (uint32_t)t,
                                   (uint32_t)id.r_global, (uint32_t)(o0 >> 3), z);
 #endif
 #pragma unroll
-              for (int q = 0; q < 8; q += 2) my_noise[(c * 4 + q / 2) * kEpiThreads] = pack_bf16(z[q], z[q + 1]);
+              for (int q = 0; q < 8; q += 2) put_noise(c * 8 + q, z[q], z[q + 1]);
             }
           }
         };
@@ -358,9 +379,14 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
                   float eps8[8];
 #pragma unroll
                   for (int q = 0; q < 8; q += 2) {
-                    const uint32_t pk = my_noise[((sub * CW + jb * 8 + q) / 2) * kEpiThreads];
-                    eps8[q] = __uint_as_float(pk << 16);             // bf16 -> fp32: low half first
-                    eps8[q + 1] = __uint_as_float(pk & 0xffff0000u);
+                    if constexpr (kPark) {
+                      const uint32_t pk = my_noise[((sub * CW + jb * 8 + q) / 2) * kEpiThreads];
+                      eps8[q] = __uint_as_float(pk << 16);           // bf16 -> fp32: low half first
+                      eps8[q + 1] = __uint_as_float(pk & 0xffff0000u);
+                    } else {
+                      eps8[q] = e_pre[sub * CW + jb * 8 + q];        // NSUB == 1 here: constant index
+                      eps8[q + 1] = e_pre[sub * CW + jb * 8 + q + 1];
+                    }
                   }
 #pragma unroll
                   for (int q = 0; q < 8; ++q) {
@@ -478,6 +504,9 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
 
         constexpr int kRsStride = NTILES * 128;
         uint32_t* my_rs = rs_smem + j * 128 + r;            // cum, costsum, cmask lo / hi, dist, cost, done
+        RowScore rs_reg;                                    // the same in registers (latency variant)
+        rs_reg.cum = 0.0f; rs_reg.costsum = 0.0f; rs_reg.cmask = 0ull; rs_reg.done = false;
+        rs_reg.dist = 0.0f; rs_reg.cost = 0.0f;
         prefetch_actions(0);
         state_pass(std::true_type{}, std::false_type{}, 0, 0);
         if (issuer) mbar_wait(bar_w, 0);                 // weights have landed before the first MMA
@@ -485,10 +514,16 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
         if (cgp == 0) {
           float d0, c0;
           combine(d0, c0);
-          my_rs[0] = 0u; my_rs[kRsStride] = 0u; my_rs[2 * kRsStride] = 0u; my_rs[3 * kRsStride] = 0u;
-          my_rs[4 * kRsStride] = __float_as_uint(d0);
-          my_rs[5 * kRsStride] = __float_as_uint(c0);
-          my_rs[6 * kRsStride] = 0u;
+          if constexpr (kPark) {
+            my_rs[0] = 0u; my_rs[kRsStride] = 0u; my_rs[2 * kRsStride] = 0u; my_rs[3 * kRsStride] = 0u;
+            my_rs[4 * kRsStride] = __float_as_uint(d0);
+            my_rs[5 * kRsStride] = __float_as_uint(c0);
+            my_rs[6 * kRsStride] = 0u;
+            my_rs[7 * kRsStride] = (uint32_t)id.out;        // output slot of this row, needed again at the end
+          } else {
+            rs_reg.dist = d0;
+            rs_reg.cost = c0;
+          }
         }
         // (the partials are next written after the tile has passed L more tile barriers, which the
         //  group-0 threads reading here reach only after combine())
@@ -544,13 +579,15 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
           if (cgp == 0) {
             float next_dist, next_cost;
             combine(next_dist, next_cost);
-            RowScore rs;
-            rs.cum = __uint_as_float(my_rs[0]);
-            rs.costsum = __uint_as_float(my_rs[kRsStride]);
-            rs.cmask = (uint64_t)my_rs[2 * kRsStride] | ((uint64_t)my_rs[3 * kRsStride] << 32);
-            rs.dist = __uint_as_float(my_rs[4 * kRsStride]);
-            rs.cost = __uint_as_float(my_rs[5 * kRsStride]);
-            rs.done = my_rs[6 * kRsStride] != 0u;
+            RowScore rs = rs_reg;
+            if constexpr (kPark) {
+              rs.cum = __uint_as_float(my_rs[0]);
+              rs.costsum = __uint_as_float(my_rs[kRsStride]);
+              rs.cmask = (uint64_t)my_rs[2 * kRsStride] | ((uint64_t)my_rs[3 * kRsStride] << 32);
+              rs.dist = __uint_as_float(my_rs[4 * kRsStride]);
+              rs.cost = __uint_as_float(my_rs[5 * kRsStride]);
+              rs.done = my_rs[6 * kRsStride] != 0u;
+            }
             const bool goal = rs.dist <= sc.goal_threshold;
             const float rew = step_reward(sc, rs.dist, next_dist, goal);
             if (done_first) {                                  // safe_cem_mpc.py:87-93
@@ -563,20 +600,33 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
               rs.done = rs.done || goal;
             }
             rs.costsum += rs.cost;
-            my_rs[0] = __float_as_uint(rs.cum);
-            my_rs[kRsStride] = __float_as_uint(rs.costsum);
-            my_rs[2 * kRsStride] = (uint32_t)rs.cmask;
-            my_rs[3 * kRsStride] = (uint32_t)(rs.cmask >> 32);
-            my_rs[4 * kRsStride] = __float_as_uint(next_dist);
-            my_rs[5 * kRsStride] = __float_as_uint(next_cost);
-            my_rs[6 * kRsStride] = rs.done ? 1u : 0u;
+            if constexpr (kPark) {
+              my_rs[0] = __float_as_uint(rs.cum);
+              my_rs[kRsStride] = __float_as_uint(rs.costsum);
+              my_rs[2 * kRsStride] = (uint32_t)rs.cmask;
+              my_rs[3 * kRsStride] = (uint32_t)(rs.cmask >> 32);
+              my_rs[4 * kRsStride] = __float_as_uint(next_dist);
+              my_rs[5 * kRsStride] = __float_as_uint(next_cost);
+              my_rs[6 * kRsStride] = rs.done ? 1u : 0u;
+            } else {
+              rs.dist = next_dist;
+              rs.cost = next_cost;
+              rs_reg = rs;
+            }
           }
           TL(43);
         }
         if (cgp == 0 && row_ok && prm.row_return != nullptr) {
-          prm.row_return[id.out] = __uint_as_float(my_rs[0]);
-          prm.row_costmask[id.out] = (uint64_t)my_rs[2 * kRsStride] | ((uint64_t)my_rs[3 * kRsStride] << 32);
-          prm.row_costsum[id.out] = __uint_as_float(my_rs[kRsStride]);
+          if constexpr (kPark) {
+            const uint32_t out_slot = my_rs[7 * kRsStride];
+            prm.row_return[out_slot] = __uint_as_float(my_rs[0]);
+            prm.row_costmask[out_slot] = (uint64_t)my_rs[2 * kRsStride] | ((uint64_t)my_rs[3 * kRsStride] << 32);
+            prm.row_costsum[out_slot] = __uint_as_float(my_rs[kRsStride]);
+          } else {
+            prm.row_return[id.out] = rs_reg.cum;
+            prm.row_costmask[id.out] = rs_reg.cmask;
+            prm.row_costsum[id.out] = rs_reg.costsum;
+          }
         }
       }
     }
