@@ -210,10 +210,6 @@ __global__ void __launch_bounds__(kSelectThreads) select_elites_kernel(SelectPar
     const int gsh = i / p.N_local, il = i - gsh * p.N_local;
     return reinterpret_cast<const float2*>(p.pairs_all)[((long)gsh * p.S + s) * p.N_local + il];
   };
-  auto key_of = [&](int i) {
-    const float2 pr = load_pair(i);
-    return pair_key(p.objective, pr.x, pr.y, p.c_max);
-  };
 
   // ---- stage the 64-bit order keys once (L2-resident scratch) and find their range --------------
   __shared__ unsigned long long sh_kmin, sh_kmax;
