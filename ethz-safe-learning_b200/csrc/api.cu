@@ -674,7 +674,7 @@ extern "C" int simba_planner_create(simba_model_t* model, const simba_planner_co
       !rollout_tc_supported(mc.obs_dim, mc.act_dim, mc.n_layers, mc.units, cfg->horizon) &&
       !rollout_tc_wide_supported(mc.obs_dim, mc.act_dim, mc.n_layers, mc.units, cfg->horizon))
     return fail(SIMBA_ERR_UNSUPPORTED,
-                "bf16 tcgen05 rollout covers units <= 128 (obs_dim <= 60, obs_dim+act_dim <= 64) and "
+                "bf16 tcgen05 rollout covers units <= 128 (obs_dim <= 60, obs_dim+act_dim <= 64, <= 5 layers) and "
                 "wide models with 128 < units <= 440 (obs_dim+act_dim <= 62, 1..6 layers); "
                 "use precision fp32 for this shape");
   int rc = validate_scorer(cfg->scorer, mc.obs_dim);
@@ -693,7 +693,8 @@ extern "C" int simba_planner_create(simba_model_t* model, const simba_planner_co
   if (rc != SIMBA_OK) { delete p; return rc; }
   p->tile_rows = cfg->precision == SIMBA_PREC_BF16_TC ? kTcTileRows : kF32TileRows;
   build_tiles(p->geom, p->tile_rows, p->tiles);
-  if (cfg->precision == SIMBA_PREC_BF16_TC && mc.units <= 128 && p->tiles.size() > 148) {
+  if (cfg->precision == SIMBA_PREC_BF16_TC && mc.units <= 128 && p->tiles.size() > 148 &&
+      rollout_tc_two_tiles_fit(mc.n_layers, cfg->scorer.n_constraints)) {
     // more tiles than SMs: two tiles per CTA so one tile's MMAs overlap the other's epilogue
     p->tiles_per_cta = 2;
     build_tiles(p->geom, p->tile_rows, p->tiles, 2);

@@ -65,6 +65,7 @@ size_t rollout_f32_smem_bytes(const RolloutParams& prm);
 cudaError_t launch_rollout_f32(const RolloutParams& prm, int n_tiles, cudaStream_t stream);
 cudaError_t launch_rollout_tc(const RolloutParams& prm, int n_tiles, cudaStream_t stream);
 bool rollout_tc_supported(int O, int A, int L, int U, int H);
+bool rollout_tc_two_tiles_fit(int L, int n_constraints);
 cudaError_t launch_rollout_tc_wide(const RolloutParams& prm, int n_tiles, cudaStream_t stream);
 bool rollout_tc_wide_supported(int O, int A, int L, int U, int H);
 int rollout_tc_wide_units(int U);                  // U rounded up to a multiple of 16

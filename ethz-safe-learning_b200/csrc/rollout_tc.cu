@@ -106,8 +106,9 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
   uint32_t* noise_smem = reinterpret_cast<uint32_t*>(part_smem + NTILES * Q * nparts * 128);
   // running objective of every rollout row (RowScore fields, field-major): only one of the Q threads of a
   // row scores, and only once per step, so the seven words live here instead of in registers
-  uint32_t* rs_smem = noise_smem + (OW / 2) * kEpiThreads;                 // [8][NTILES * 128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(rs_smem + 8 * NTILES * 128);
+  uint32_t* rs_smem = noise_smem + (NTILES > 1 ? (OW / 2) * kEpiThreads : 0);   // [8][NTILES * 128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rs_smem + (NTILES > 1 ? 8 * NTILES * 128 : 0));
+  // (both parking areas exist only in the two-tile variant, see kPark below)
   // bars[0] = weights landed; bars[1 + j] = accumulator ready (tile j)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * NTILES);
   TileInfo* tinfo = reinterpret_cast<TileInfo*>(tmem_slot + 2);
@@ -638,21 +639,32 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-bool rollout_tc_supported(int O, int A, int L, int U, int H) {
-  // narrower hidden layers run zero-padded to 128 units (simba_model_commit pads the images)
-  return U >= 1 && U <= kU && O >= 1 && O <= kMaxO && O + A <= 64 && A <= 4 && L >= 1 && L <= 6 && H >= 1 && H <= 64;
-}
-
 static size_t tc_smem_bytes(int L, int ntiles, int q, int nparts) {
   size_t b = (size_t)kAtomBytes + (size_t)L * 2 * kAtomBytes;      // weights
   b += (size_t)(L + 1) * 4096 + 4096;                              // bias K-blocks + ones tile
   b += 128 * sizeof(float);                                        // scaler
   b += kParts * 64 * sizeof(float);                                // slice penalty table
   b += (size_t)ntiles * q * nparts * 128 * sizeof(float);          // partial minima exchange
-  b += (size_t)(64 / q / 2) * (ntiles * q * 128) * sizeof(uint32_t);   // bf16x2 noise of the current step
-  b += (size_t)8 * ntiles * 128 * sizeof(uint32_t);                    // per-row running objective
+  if (ntiles > 1) {                                                // parking areas of the two-tile variant
+    b += (size_t)(64 / q / 2) * (ntiles * q * 128) * sizeof(uint32_t);   // bf16x2 noise of the current step
+    b += (size_t)8 * ntiles * 128 * sizeof(uint32_t);                    // per-row running objective
+  }
   b += (1 + 2 * ntiles) * sizeof(uint64_t) + 2 * sizeof(uint32_t) + ntiles * sizeof(TileInfo);
   return b + 1024;                                                 // alignment slack
+}
+
+constexpr size_t kMaxSmem = 227 * 1024;
+
+bool rollout_tc_supported(int O, int A, int L, int U, int H) {
+  // narrower hidden layers run zero-padded to 128 units (simba_model_commit pads the images); the
+  // member's whole weight set must fit in shared memory next to the one-tile variant's buffers
+  return U >= 1 && U <= kU && O >= 1 && O <= kMaxO && O + A <= 64 && A <= 4 && L >= 1 && H >= 1 && H <= 64 &&
+         tc_smem_bytes(L, 1, 4, kParts) + 1024 <= kMaxSmem;
+}
+
+// whether the two-tile throughput variant (and its shared-memory parking areas) fits for this depth
+bool rollout_tc_two_tiles_fit(int L, int n_constraints) {
+  return tc_smem_bytes(L, 2, 2, 1 + n_constraints) + 1024 <= kMaxSmem;
 }
 
 template <int NTILES, int Q>

@@ -24,7 +24,9 @@ torch = pytest.importorskip("torch")
                                       ('tiny', dict(U=144, L=4)), ('c5', dict(H=10)), ('c5', {}),
                                       # zero-padded widths: 64 / 72 -> 128 (rollout_tc.cu), 130 -> 144 and 200 -> 208 (wide)
                                       ('tiny', dict(U=64)), ('tiny', dict(U=72, L=3)), ('tiny', dict(U=130, L=2)),
-                                      ('tiny', dict(U=200, L=3)), ('tiny', dict(U=256, L=1))])
+                                      ('tiny', dict(U=200, L=3)), ('tiny', dict(U=256, L=1)),
+                                      # deepest model whose weights fit in shared memory (one tile per CTA only)
+                                      ('tiny', dict(L=5)), ('tiny', dict(L=5, S=1, N=2600, P=8, E=2, K=10, H=3))])
 def test_tc_rollout_rows_close_to_oracle(cfg, over):
     from simba_b200 import _lib
     lib = _lib.load()
