@@ -672,10 +672,11 @@ extern "C" int simba_planner_create(simba_model_t* model, const simba_planner_co
     return fail(SIMBA_ERR_BAD_CONFIG, "precision %d unknown", cfg->precision);
   if (cfg->precision == SIMBA_PREC_BF16_TC &&
       !rollout_tc_supported(mc.obs_dim, mc.act_dim, mc.n_layers, mc.units, cfg->horizon) &&
-      !rollout_tc_wide_supported(mc.obs_dim, mc.act_dim, mc.n_layers, mc.units, cfg->horizon))
+      !(rollout_tc_wide_supported(mc.obs_dim, mc.act_dim, mc.n_layers, mc.units, cfg->horizon) &&
+        rollout_tc_wide_fits(mc.n_layers, mc.units, cfg->scorer.n_constraints)))
     return fail(SIMBA_ERR_UNSUPPORTED,
                 "bf16 tcgen05 rollout covers units <= 128 (obs_dim <= 60, obs_dim+act_dim <= 64, <= 5 layers) and "
-                "wide models with 128 < units <= 440 (obs_dim+act_dim <= 62, 1..6 layers); "
+                "wide models with 128 < units <= ~416 (less with several constrained lidars; obs_dim+act_dim <= 62); "
                 "use precision fp32 for this shape");
   int rc = validate_scorer(cfg->scorer, mc.obs_dim);
   if (rc != SIMBA_OK) return rc;

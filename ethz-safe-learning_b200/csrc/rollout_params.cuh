@@ -68,6 +68,7 @@ bool rollout_tc_supported(int O, int A, int L, int U, int H);
 bool rollout_tc_two_tiles_fit(int L, int n_constraints);
 cudaError_t launch_rollout_tc_wide(const RolloutParams& prm, int n_tiles, cudaStream_t stream);
 bool rollout_tc_wide_supported(int O, int A, int L, int U, int H);
+bool rollout_tc_wide_fits(int L, int U, int n_constraints);
 int rollout_tc_wide_units(int U);                  // U rounded up to a multiple of 16
 int64_t rollout_tc_wide_member_bytes(int L, int U);   // U = padded units
 

@@ -1,4 +1,4 @@
-// bf16 tcgen05 rollout + scoring kernel for WIDE ensembles (128 < units <= 448, e.g. the 4x400
+// bf16 tcgen05 rollout + scoring kernel for WIDE ensembles (128 < units <= 416, e.g. the 4x400
 // model of BASELINE configs[4]) — same contract as rollout_tc.cu / rollout_f32.cu.
 //
 // A member's weights (1.2 MB for 4x400) no longer fit in shared memory, and a 400-column fp32
@@ -579,12 +579,20 @@ __global__ void __launch_bounds__(kWideThreads, 1) rollout_tc_wide_kernel(const 
 }
 
 // ---- host side ------------------------------------------------------------------------------------
+static size_t wide_smem_bytes(int L, int U, int nparts);
+
 // widths that are not a multiple of 16 run zero-padded to the next one (rollout_tc_wide_units)
 int rollout_tc_wide_units(int U) { return (U + 15) / 16 * 16; }
 
+// shape check used when the weight images are packed (no scorer yet: one constraint slot assumed)
 bool rollout_tc_wide_supported(int O, int A, int L, int U, int H) {
-  return U > 128 && rollout_tc_wide_units(U) <= 440 && O >= 1 && O <= 60 && O + A + 2 <= 64 && A <= 4 &&
-         L >= 1 && L <= 6 && H >= 1 && H <= 64;
+  return U > 128 && rollout_tc_wide_units(U) <= 448 - 2 && O >= 1 && O <= 60 && O + A + 2 <= 64 && A <= 4 &&
+         L >= 1 && L <= 6 && H >= 1 && H <= 64 && wide_smem_bytes(L, rollout_tc_wide_units(U), 1) <= 227 * 1024;
+}
+
+// the A tile, the two-stage weight ring and the per-constraint exchange buffers must share 227 KB
+bool rollout_tc_wide_fits(int L, int U, int n_constraints) {
+  return wide_smem_bytes(L, rollout_tc_wide_units(U), 1 + n_constraints) <= 227 * 1024;
 }
 
 int64_t rollout_tc_wide_member_bytes(int L, int U) {

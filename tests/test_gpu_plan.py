@@ -173,13 +173,14 @@ def test_fused_update_kernel_is_bit_identical_to_separate_kernels(precision):
 
 def test_wide_model_c5_reward_only_vs_safety_aware():
     """BASELINE configs[4]: 10-member ensemble, 4x400 hidden, horizon 50, on the fp32 kernel (exact
-    parity contract). Widths neither tcgen05 kernel covers (> 440) report SIMBA_ERR_UNSUPPORTED for bf16."""
+    parity contract). Widths neither tcgen05 kernel covers (> 416) report SIMBA_ERR_UNSUPPORTED for bf16."""
     from simba_b200 import SimbaError, _lib, synthetic
     c = helpers.workload('c5', N=40, K=5, I=2)                  # full model / horizon, small population
     z, eps, zf = synthetic.make_draws(c['I'], 1, c['N'], c['H'], c['A'], c['P'], c['O'])
-    with pytest.raises(SimbaError) as e:
-        helpers.cuda_policy(helpers.workload('tiny', U=500), 'penalty', precision='bf16').build()
-    assert e.value.code == -6
+    for width in (432, 500):          # the A tile + weight ring of the wide kernel stop fitting above 416
+        with pytest.raises(SimbaError) as e:
+            helpers.cuda_policy(helpers.workload('tiny', U=width), 'penalty', precision='bf16').build()
+        assert e.value.code == -6
     for objective in ('reward', 'penalty'):
         pol = helpers.cuda_policy(c, objective, precision='fp32')
         pol.set_external_draws(z, eps, zf)
