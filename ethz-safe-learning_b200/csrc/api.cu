@@ -239,6 +239,15 @@ extern "C" int simba_model_commit(simba_model_t* m) {
     act_rows = std::max(act_rows, std::max(Kp, Np));
   }
   m->n_chunks = n_chunks; m->bias_stride = bias_stride; m->act_rows = act_rows;
+  {
+    // the fp32 kernel keeps two activation tiles [act_rows x 32 rows] in shared memory: very wide
+    // layers (> ~780 units) do not fit and are rejected here rather than at the first launch
+    RolloutParams probe{};
+    probe.g.O = O; probe.g.A = c.act_dim; probe.act_rows = act_rows;
+    if (rollout_f32_smem_bytes(probe) > 227 * 1024)
+      return fail(SIMBA_ERR_UNSUPPORTED, "units %d: the rollout kernels keep a row tile's activations in "
+                  "shared memory, which holds at most ~780 hidden units", U);
+  }
   std::vector<float> w((size_t)E * n_chunks * KC * NB, 0.0f), b((size_t)E * bias_stride, 0.0f);
   for (int e = 0; e < E; ++e) {
     size_t chunk = (size_t)e * n_chunks;

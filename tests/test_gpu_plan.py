@@ -181,6 +181,12 @@ def test_wide_model_c5_reward_only_vs_safety_aware():
         with pytest.raises(SimbaError) as e:
             helpers.cuda_policy(helpers.workload('tiny', U=width), 'penalty', precision='bf16').build()
         assert e.value.code == -6
+    with pytest.raises(SimbaError) as e:              # no kernel holds a 1024-wide activation tile
+        helpers.cuda_policy(helpers.workload('tiny', U=1024, L=1), 'penalty', precision='fp32').build()
+    assert e.value.code == -6
+    wide = helpers.cuda_policy(helpers.workload('tiny', U=768, L=1), 'penalty', precision='fp32')
+    a_w, s_w = wide.do_generate_action(helpers.workload('tiny', U=768, L=1)['state'], seed=1)
+    assert np.all(np.isfinite(a_w)) and np.isfinite(s_w)    # the widest model the fp32 kernel takes
     for objective in ('reward', 'penalty'):
         pol = helpers.cuda_policy(c, objective, precision='fp32')
         pol.set_external_draws(z, eps, zf)
