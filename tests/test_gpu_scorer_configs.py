@@ -1,0 +1,114 @@
+"""Rollout kernels under non-default SafetyGymStateScorer configurations (safety_gym.py:145-166,
+:110-143): several constrained lidars (vases + hazards, reference order), additive costs
+(`constrain_indicator=False`), and different reward shaping constants — every kernel (fp32, bf16 with
+128 units, bf16 wide) against the oracle's rows."""
+import numpy as np
+import pytest
+
+from oracle import simba_oracle as so
+from tests import helpers
+from tests.test_gpu_kernels import _oracle_rows, dev, P
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+CONFIGS = {
+    'two_constraints': dict(constrain_vases=True),
+    'additive_cost': dict(constrain_indicator=False),                  # one class: cost in {0, 1} either way
+    'reward_shaping': dict(reward_distance=3.0, reward_goal=2.0, reward_clip=0.05),
+    'vases_only': dict(constrain_vases=True, constrain_hazards=False, vases_size=0.3),
+}
+
+
+def _rows(c, scorer_config, precision):
+    from simba_b200 import _lib
+    lib = _lib.load()
+    pol = helpers.cuda_policy(c, 'penalty', precision=precision, scorer_config=scorer_config)
+    pl = pol._ensure_planner()
+    pl_o = helpers.oracle_planner(c, 'penalty', scorer_config=scorer_config)
+    rng = np.random.default_rng(16)
+    acts = rng.uniform(-1, 1, (c['N'], c['H'], c['A'])).astype(np.float32)
+    eps = rng.standard_normal((c['H'], c['P'] * c['N'], c['O'])).astype(np.float32)
+    B = c['P'] * c['N']
+    ret = torch.empty(B, dtype=torch.float32, device='cuda')
+    mask = torch.empty(B, dtype=torch.int64, device='cuda')
+    csum = torch.empty(B, dtype=torch.float32, device='cuda')
+    d_state, d_acts, d_eps = dev(c['state'][None]), dev(acts[None]), dev(eps[None])
+    _lib.check(lib.simba_rollout_score(pl, P(d_state), P(d_acts), P(d_eps), 0, 0, None, P(ret), P(mask),
+                                       P(csum), None))
+    torch.cuda.synchronize()
+    traj, cum0, mask0, csum0 = _oracle_rows(c, pl_o, acts, eps, 'penalty')
+    return (ret.cpu().numpy(), mask.cpu().numpy().view(np.uint64), csum.cpu().numpy()), (traj, cum0, mask0, csum0)
+
+
+@pytest.mark.parametrize('name', sorted(CONFIGS))
+def test_fp32_rows_with_scorer_config(name):
+    cfg = CONFIGS[name]
+    c = helpers.workload('c1', N=60)
+    (ret, mask, csum), (traj, cum0, mask0, csum0) = _rows(c, cfg, 'fp32')
+    sc = so.Scorer(cfg, c['table'])
+    frag = np.zeros(len(ret), bool)                      # rows with a hard decision within 1e-4 of its threshold
+    for t in range(c['H'] + 1):
+        frag |= np.abs(sc.goal_distance_metric(traj[:, t]) - np.float32(0.24)) < 1e-4
+        for lidar in ('vases', 'hazards'):
+            if sc.c['constrain_' + lidar]:
+                d = sc.closest_distance(traj[:, t][:, c['table'][lidar + '_lidar']])
+                frag |= np.abs(d - np.float32(sc.c[lidar + '_size'])) < 1e-4
+    assert frag.mean() < 0.03
+    ok = ~frag
+    assert np.allclose(ret[ok], cum0[ok], rtol=1e-4, atol=2e-5)
+    assert np.array_equal(mask[ok], mask0[ok])
+    assert np.array_equal(csum[ok], csum0[ok])
+    if name == 'reward_shaping':
+        assert np.abs(cum0).max() <= 0.05 * c['H'] + 1e-6    # every step clipped to +-0.05
+
+
+@pytest.mark.parametrize('name', sorted(CONFIGS))
+@pytest.mark.parametrize('over', [{}, dict(U=256, E=2)])
+def test_bf16_rows_with_scorer_config(name, over):
+    cfg = CONFIGS[name]
+    c = helpers.workload('c1', N=60, **over)
+    (ret, mask, csum), (traj, cum0, mask0, csum0) = _rows(c, cfg, 'bf16')
+    scale = 3.0 if name == 'reward_shaping' else 1.0
+    assert np.all(np.isfinite(ret))
+    assert np.abs(ret - cum0).mean() < 1e-2 * scale
+    assert (mask == mask0).mean() > 1.0 - 0.002 * c['H'] - 0.01
+    assert np.abs(csum - csum0).mean() < 0.05
+
+
+def test_additive_cost_over_several_classes_is_rejected_loudly():
+    """constrain_indicator=False with two constrained classes would need per-step costs of 0..2; the fused
+    kernels keep one cost bit per step, so the planner refuses instead of silently saturating."""
+    from simba_b200 import SimbaError
+    c = helpers.workload('tiny')
+    with pytest.raises(SimbaError) as e:
+        helpers.cuda_policy(c, 'penalty', precision='fp32',
+                            scorer_config=dict(constrain_vases=True, constrain_indicator=False)).build()
+    assert e.value.code == -6
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_goal_dist_observation_instead_of_goal_lidar(precision):
+    """observe_goal_dist (safety_gym.py:172-174): the goal distance is one observed scalar,
+    dist = max(obs[goal_dist], 0), instead of the closest goal-lidar bin."""
+    sensors = dict(accelerometer=3, goal_dist=1, gyro=3, hazards_lidar=16, magnetometer=3, velocimeter=3)
+    cfg = dict(observe_goal_lidar=False, observe_goal_dist=True)
+    c = helpers.workload('c1', N=60, sensors=sensors)
+    st = c['state'].copy()
+    st[c['table']['goal_dist']] = 0.6                       # start away from the goal (threshold 0.24)
+    c['state'] = st
+    (ret, mask, csum), (traj, cum0, mask0, csum0) = _rows(c, cfg, precision)
+    assert np.abs(cum0).max() > 1e-3                        # the reward signal is alive
+    if precision == 'fp32':
+        sc = so.Scorer(cfg, c['table'])
+        frag = np.zeros(len(ret), bool)
+        for t in range(c['H'] + 1):
+            frag |= np.abs(sc.goal_distance_metric(traj[:, t]) - np.float32(0.24)) < 1e-4
+            frag |= np.abs(sc.closest_distance(traj[:, t][:, c['table']['hazards_lidar']]) - np.float32(0.2)) < 1e-4
+        ok = ~frag
+        assert frag.mean() < 0.03
+        assert np.allclose(ret[ok], cum0[ok], rtol=1e-4, atol=2e-5)
+        assert np.array_equal(mask[ok], mask0[ok]) and np.array_equal(csum[ok], csum0[ok])
+    else:
+        assert np.abs(ret - cum0).mean() < 1e-2
+        assert (mask == mask0).mean() > 1.0 - 0.002 * c['H'] - 0.01
