@@ -98,7 +98,7 @@ def make_workload(cfg_name='c1', sensors=None, seed=0, mu_scale=0.05, var_bias=-
     c.update(over)
     sensors = sensors or POINTGOAL1_SENSORS
     table, O = offsets(sensors)
-    A = 2
+    A = int(c.get('A', 2))                        # action dims (the reference's point robot has 2)
     c.update(O=O, A=A, sensors=sensors, table=table)
     c['weights'] = make_weights(c['E'], c['L'], c['U'], O, A, seed=seed, mu_scale=mu_scale,
                                 var_bias=var_bias, action_gain=action_gain)
@@ -116,7 +116,7 @@ def build_policy(c, objective='penalty', precision='bf16', member_map='split', t
     from .environment_utils import ScorerEnvironment
     from .models import TransitionModel
     from .policies import CemMpc, SafeCemMpc
-    env = ScorerEnvironment(c['sensors'], scorer_config)
+    env = ScorerEnvironment(c['sensors'], scorer_config, action_low=[-1.0] * c['A'], action_high=[1.0] * c['A'])
     tm = TransitionModel('mlp_ensemble', env.observation_space, env.action_space, True,
                          sampling_propagation, ensemble_size=c['E'],
                          mlp_params=dict(n_layers=c['L'], units=c['U'], activation='tf.nn.relu',

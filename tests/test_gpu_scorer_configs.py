@@ -112,3 +112,53 @@ def test_goal_dist_observation_instead_of_goal_lidar(precision):
     else:
         assert np.abs(ret - cum0).mean() < 1e-2
         assert (mask == mask0).mean() > 1.0 - 0.002 * c['H'] - 0.01
+
+
+@pytest.mark.parametrize('A,over,precision', [
+    (1, {}, 'fp32'), (3, {}, 'fp32'), (4, {}, 'fp32'), (7, dict(sensors='simple'), 'fp32'),
+    (1, {}, 'bf16'), (3, {}, 'bf16'), (4, {}, 'bf16'),
+    (1, dict(U=256, E=2), 'bf16'), (4, dict(U=256, E=2, sensors='simple'), 'bf16')])
+def test_action_dimensions_other_than_two(A, over, precision):
+    """act_dim 1..4 on the tensor-core kernels (the action columns share the layer-0 K atom with the
+    state) and up to 16 on the fp32 kernel; the reference's robots have 2."""
+    from simba_b200 import synthetic
+    over = dict(over)
+    sensors = synthetic.POINTSIMPLEGOAL1_SENSORS if over.pop('sensors', None) == 'simple' else None
+    c = helpers.workload('c1', N=40, A=A, sensors=sensors, **over)
+    assert c['A'] == A
+    (ret, mask, csum), (traj, cum0, mask0, csum0) = _rows(c, None, precision)
+    assert np.all(np.isfinite(ret))
+    if precision == 'fp32':
+        sc = so.Scorer(None, c['table'])
+        frag = np.zeros(len(ret), bool)
+        for t in range(c['H'] + 1):
+            frag |= np.abs(sc.goal_distance_metric(traj[:, t]) - np.float32(0.24)) < 1e-4
+            frag |= np.abs(sc.closest_distance(traj[:, t][:, c['table']['hazards_lidar']]) - np.float32(0.2)) < 1e-4
+        ok = ~frag
+        assert frag.mean() < 0.03
+        assert np.allclose(ret[ok], cum0[ok], rtol=1e-4, atol=2e-5)
+        assert np.array_equal(mask[ok], mask0[ok]) and np.array_equal(csum[ok], csum0[ok])
+    else:
+        assert np.abs(ret - cum0).mean() < 1e-2
+        assert (mask == mask0).mean() > 1.0 - 0.002 * c['H'] - 0.01
+
+
+@pytest.mark.parametrize('A', [1, 3])
+def test_whole_plan_with_odd_action_dimension(A):
+    """H * A not a multiple of 4 (Philox blocks straddle candidates' ends): full CEM loop vs the oracle."""
+    from simba_b200 import _lib, synthetic
+    c = helpers.workload('tiny', A=A, H=5)
+    z, eps, zf = synthetic.make_draws(c['I'], 1, c['N'], c['H'], c['A'], c['P'], c['O'])
+    pol = helpers.cuda_policy(c, 'penalty', precision='fp32')
+    pol.set_external_draws(z, eps, zf)
+    action, score = pol.do_generate_action(c['state'])
+    tr = so.Trace()
+    a0, s0, n0 = helpers.oracle_planner(c, 'penalty').do_generate_action(c['state'], z[:, 0], eps[:, 0], zf[0], tr)
+    assert action.shape == (A,)
+    assert np.array_equal(pol.buffer(_lib.BUF_ELITE, torch.int32).cpu().numpy(), tr[-1]['elite'])
+    assert np.allclose(action, a0, rtol=1e-4, atol=1e-6) and np.isclose(score, s0, rtol=1e-4, atol=1e-5)
+    # production mode (Philox on the device) is reproducible for this shape too
+    p2 = helpers.cuda_policy(c, 'penalty', precision='bf16')
+    a1, _ = p2.do_generate_action(c['state'], seed=4)
+    a2, _ = p2.do_generate_action(c['state'], seed=4)
+    assert np.array_equal(a1, a2) and a1.shape == (A,)
