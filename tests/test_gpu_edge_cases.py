@@ -1,7 +1,7 @@
-"""Rollout kernels under non-default SafetyGymStateScorer configurations (safety_gym.py:145-166,
-:110-143): several constrained lidars (vases + hazards, reference order), additive costs
-(`constrain_indicator=False`), and different reward shaping constants — every kernel (fp32, bf16 with
-128 units, bf16 wide) against the oracle's rows."""
+"""Edge cases of the hot path on the GPU, each against the oracle: non-default SafetyGymStateScorer
+configurations (safety_gym.py:145-166, :110-143: several constrained lidars, vases only, additive flag,
+reward shaping, goal_dist observation), action dimensions other than 2, and extreme planner shapes
+(H = 1 / 64, one particle, one candidate, 16 members) — on the fp32, bf16 and wide bf16 kernels."""
 import numpy as np
 import pytest
 
@@ -162,3 +162,25 @@ def test_whole_plan_with_odd_action_dimension(A):
     a1, _ = p2.do_generate_action(c['state'], seed=4)
     a2, _ = p2.do_generate_action(c['state'], seed=4)
     assert np.array_equal(a1, a2) and a1.shape == (A,)
+
+
+@pytest.mark.parametrize('over', [dict(H=1), dict(H=64, N=16, K=4), dict(P=1, E=1), dict(N=1, K=1, P=8),
+                                  dict(P=60, E=3, N=10, K=2), dict(E=16, P=16, N=8, K=2, I=2)])
+def test_extreme_planner_shapes(over):
+    """Maximum horizon (64: every bit of the cost mask), one step, one particle, one candidate, many members
+    — whole plans on the fp32 kernel against the oracle, and the bf16 kernel must stay finite and
+    reproducible on the same shapes."""
+    from simba_b200 import _lib, synthetic
+    c = helpers.workload('tiny', **over)
+    z, eps, zf = synthetic.make_draws(c['I'], 1, c['N'], c['H'], c['A'], c['P'], c['O'])
+    pol = helpers.cuda_policy(c, 'penalty', precision='fp32')
+    pol.set_external_draws(z, eps, zf)
+    action, score = pol.do_generate_action(c['state'])
+    tr = so.Trace()
+    a0, s0, n0 = helpers.oracle_planner(c, 'penalty').do_generate_action(c['state'], z[:, 0], eps[:, 0], zf[0], tr)
+    assert np.array_equal(pol.buffer(_lib.BUF_ELITE, torch.int32).cpu().numpy(), tr[-1]['elite'])
+    assert np.allclose(action, a0, rtol=1e-4, atol=1e-6) and np.isclose(score, s0, rtol=1e-4, atol=1e-4)
+    p2 = helpers.cuda_policy(c, 'penalty', precision='bf16')
+    a1, s1 = p2.do_generate_action(c['state'], seed=4)
+    a2, s2 = p2.do_generate_action(c['state'], seed=4)
+    assert np.all(np.isfinite(a1)) and np.isfinite(s1) and np.array_equal(a1, a2) and s1 == s2
