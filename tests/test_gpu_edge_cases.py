@@ -184,3 +184,33 @@ def test_extreme_planner_shapes(over):
     a1, s1 = p2.do_generate_action(c['state'], seed=4)
     a2, s2 = p2.do_generate_action(c['state'], seed=4)
     assert np.all(np.isfinite(a1)) and np.isfinite(s1) and np.array_equal(a1, a2) and s1 == s2
+
+
+def test_handles_release_their_device_memory():
+    """Model, planner and trainer handles own raw cudaMalloc memory (not torch's): creating and dropping
+    them repeatedly must give it all back."""
+    import gc
+    from simba_b200.models import MlpEnsemble
+    c = helpers.workload('c1', S=4)
+    rng = np.random.default_rng(0)
+    x = rng.uniform(0, 1, (c['E'], 64, c['O'] + c['A'])).astype(np.float32)
+    y = rng.normal(0, 0.1, (c['E'], 64, c['O'])).astype(np.float32)
+
+    def cycle():
+        for precision in ('fp32', 'bf16'):
+            pol = helpers.cuda_policy(c, 'penalty', precision=precision, n_states=4)
+            pol.do_generate_action(c['state'], seed=1)
+            del pol
+        ens = MlpEnsemble(c['O'] + c['A'], c['O'], c['E'], mlp_params=dict(n_layers=c['L'], units=c['U']))
+        ens.training_step(x, y)
+        ens.forward(x[0][:60])                            # 60 rows: tf.split needs B % E == 0
+        del ens
+        gc.collect()
+        torch.cuda.synchronize()
+
+    cycle()                                               # warm-up: context, module loading, torch caches
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(8):
+        cycle()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 32 * 1024 * 1024, (free0, free1)
