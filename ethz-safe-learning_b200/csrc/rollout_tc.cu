@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
               if (kSample) tmem_ld<CW>(t_lane + 64 + oc, vv);
               tmem_ld<CW>(t_state + oc, st);
               tmem_ld_wait();
+              if (sub == 0) TL(44);
 #pragma unroll
               for (int jb = 0; jb < CW / 8; ++jb) {             // one Philox NOISE block = 8 outputs
                 const int o0 = oc + jb * 8;
@@ -412,6 +413,7 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
 #pragma unroll
               for (int i = 0; i < CW; ++i) st[i] = __float_as_uint(sv[i]);
               tmem_st<CW>(t_state + oc, st);
+              if (sub == 0) TL(45);
             }
             // ---- partial lidar minima, only for chunks that intersect a slice -----------------
 #ifdef ABL_NO_SCORE
@@ -481,7 +483,9 @@ __global__ void __launch_bounds__(NTILES* Q * 128, 1) rollout_tc_kernel(const Ro
               tmem_st<CW / 2>(t_a + oc / 2, pk);            // K elements [oc, oc + CW) of the layer-0 input
             }
           }
+          TL(46);
           tmem_st_wait();
+          TL(47);
           part[0] = gmin;
 #pragma unroll
           for (int q = 0; q < SIMBA_MAX_CONSTRAINTS; ++q)

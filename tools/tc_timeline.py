@@ -44,5 +44,7 @@ for who, name in ((0, 'issuer (warp 0)'), (1, 'last warp of tile')):
             ev[40] - base, ev[41] - base, ev[42] - base, ev[43] - base, t[who, step + 1][0] - base))
         line.append("| issue detail (st_wait, barrier) per layer: " + ' '.join(
             "%d:(%d,%d)" % (l, ev[48 + l] - base, ev[54 + l] - base) for l in range(L + 1)))
+        line.append("| head detail: ld_wait->%d state_st->%d before_st_wait->%d after->%d" % tuple(
+            ev[k] - base for k in (44, 45, 46, 47)))
         rows.append(' '.join(line))
     print('\n'.join(rows[:6]))
