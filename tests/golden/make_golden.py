@@ -29,3 +29,32 @@ for objective in ('reward', 'penalty', 'least_cost', 'feasible_first'):
         out['%s_cost_%d' % (objective, it)] = rec['cost']
 np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'oracle_tiny_plan.npz'), **out)
 print("wrote", len(out), "arrays")
+
+# ---- training step (oracle/train_oracle.py): three steps of a tiny ensemble, with and without dropout ----
+from oracle import train_oracle as T  # noqa: E402
+
+tout = {}
+for tag, rate in (('plain', 0.0), ('dropout', 0.25)):
+    rng = np.random.default_rng(7)
+    members = []
+    for _ in range(2):
+        arrays, fan = [], 6
+        for _ in range(2):
+            arrays += [rng.normal(0, 0.4, (fan, 8)).astype(np.float32), rng.normal(0, 0.1, 8).astype(np.float32)]
+            fan = 8
+        for _ in range(2):
+            arrays += [rng.normal(0, 0.4, (8, 4)).astype(np.float32), rng.normal(0, 0.1, 4).astype(np.float32)]
+        members.append(arrays)
+    tr = T.EnsembleTrainer(members, batch_size=5, learning_rate=1e-2, learning_rate_schedule=True, training_steps=2,
+                           train_epochs=3, dropout_rate=rate, dropout_seed=11)
+    losses = []
+    for s in range(3):
+        x = rng.uniform(0, 1, (2, 5, 6)).astype(np.float32)
+        y = rng.normal(0, 0.2, (2, 5, 4)).astype(np.float32)
+        losses.append(tr.training_step(x, y))
+    tout[tag + '_losses'] = np.asarray(losses, np.float32)
+    for e, net in enumerate(tr.nets):
+        for i, a in enumerate(net.arrays):
+            tout['%s_member%d_var%d' % (tag, e, i)] = a
+np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'oracle_tiny_train.npz'), **tout)
+print("wrote", len(tout), "training arrays")

@@ -122,3 +122,32 @@ def test_dropout_gradients_and_mask_statistics():
     assert not np.array_equal(m, philox.dropout_keep(9, 4, 1, 2, 256, 400, 0.25))      # new mask every step
     assert not np.array_equal(m, philox.dropout_keep(9, 3, 0, 2, 256, 400, 0.25))      # and per member
     assert np.array_equal(philox.dropout_keep(9, 3, 1, 2, 256, 400, 0.0), np.ones((256, 400), bool))
+
+
+def test_training_oracle_matches_committed_golden():
+    """Self-golden (tests/golden/make_golden.py): three training steps of a tiny ensemble with the epoch
+    schedule, with and without dropout — freezes today's oracle so later edits cannot drift silently."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'oracle_tiny_train.npz'))
+    for tag, rate in (('plain', 0.0), ('dropout', 0.25)):
+        rng = np.random.default_rng(7)
+        members = []
+        for _ in range(2):
+            arrays, fan = [], 6
+            for _ in range(2):
+                arrays += [rng.normal(0, 0.4, (fan, 8)).astype(np.float32), rng.normal(0, 0.1, 8).astype(np.float32)]
+                fan = 8
+            for _ in range(2):
+                arrays += [rng.normal(0, 0.4, (8, 4)).astype(np.float32), rng.normal(0, 0.1, 4).astype(np.float32)]
+            members.append(arrays)
+        tr = T.EnsembleTrainer(members, batch_size=5, learning_rate=1e-2, learning_rate_schedule=True,
+                               training_steps=2, train_epochs=3, dropout_rate=rate, dropout_seed=11)
+        losses = []
+        for s in range(3):
+            x = rng.uniform(0, 1, (2, 5, 6)).astype(np.float32)
+            y = rng.normal(0, 0.2, (2, 5, 4)).astype(np.float32)
+            losses.append(tr.training_step(x, y))
+        np.testing.assert_allclose(np.asarray(losses, np.float32), gold[tag + '_losses'], rtol=1e-6)
+        for e, net in enumerate(tr.nets):
+            for i, a in enumerate(net.arrays):
+                np.testing.assert_allclose(a, gold['%s_member%d_var%d' % (tag, e, i)], rtol=1e-6, atol=1e-7)
