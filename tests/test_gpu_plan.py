@@ -263,3 +263,39 @@ def test_weight_and_scaler_updates_reach_an_already_used_planner():
         a4, s4 = pol.do_generate_action(c['state'], seed=9)
         a5, s5 = fresh.do_generate_action(c['state'], seed=9)
         assert np.array_equal(a4, a5) and s4 == s5 and not np.array_equal(a4, a2)
+
+
+def _reference_cases():
+    from tests.test_reference_golden import PLANS
+    for cfg in ('tiny', 'c1'):
+        for tag in PLANS:
+            if cfg == 'tiny' or tag in ('reward', 'penalty'):
+                yield cfg, tag
+
+
+@pytest.mark.parametrize("cfg,tag", list(_reference_cases()))
+def test_plan_matches_unmodified_reference_code_fp32(cfg, tag):
+    """The CUDA planner against fixtures produced by the reference's own CemMpc / SafeCemMpc code
+    (tests/golden/reference_*.npz, see tests/golden/make_reference_golden.py), identical weights, state
+    and draws: elite indices exact, scores / refit / action within 1e-4 relative (north_star)."""
+    import os
+    from simba_b200 import _lib, synthetic
+    from tests.test_reference_golden import GOLD, PLANS
+    g = np.load(os.path.join(GOLD, 'reference_%s_plan.npz' % cfg))
+    objective, kw = PLANS[tag]
+    c = helpers.workload(cfg)
+    z, eps, zf = synthetic.make_draws(c['I'], 1, c['N'], c['H'], c['A'], c['P'], c['O'])
+    pol = helpers.cuda_policy(c, objective, precision='fp32', **kw)
+    pol.set_external_draws(z, eps, zf)
+    action, score = pol.do_generate_action(c['state'])
+    n = int(g[tag + '_iterations'])
+    assert int(pol.iterations_run[0]) == n
+    elite = pol.buffer(_lib.BUF_ELITE, torch.int32).cpu().numpy()
+    assert np.array_equal(elite, g['%s_elite_%d' % (tag, n - 1)])
+    if kw.get('smoothing', 0.0) == 0.0:
+        mu = pol.buffer(_lib.BUF_MU).cpu().numpy().reshape(c['H'], c['A'])
+        sg = pol.buffer(_lib.BUF_SIGMA).cpu().numpy().reshape(c['H'], c['A'])
+        assert np.allclose(mu, g['%s_mean_%d' % (tag, n - 1)], rtol=1e-4, atol=1e-6)
+        assert np.allclose(sg, np.sqrt(g['%s_var_%d' % (tag, n - 1)]), rtol=1e-4, atol=1e-6)
+    assert np.isclose(score, g[tag + '_score'], rtol=1e-4, atol=1e-5)
+    assert np.allclose(action, g[tag + '_action'], rtol=1e-4, atol=1e-6)
