@@ -66,6 +66,13 @@ extern "C" int simba_device_check(void) {
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+static float bf16_to_f32(uint16_t h) {
+  const uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
 static uint16_t f32_to_bf16_rne(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);
@@ -293,6 +300,12 @@ extern "C" int simba_model_commit(simba_model_t* m) {
       for (int l = 0; l <= L; ++l) {
         const int K = l == 0 ? IN : U;
         auto weight = [&](int k, int n) -> float {     // n = tile row (output feature)
+          if (l == 0 && IN + 2 <= 64 && (k == IN || k == IN + 1) && n < U) {
+            // layer 0 carries its bias in the K padding: the kernel feeds the constant 1 at k = IN, IN + 1
+            const float bv = m->biases[e * (L + 2)][n];
+            const float hi = bf16_to_f32(f32_to_bf16_rne(bv));
+            return k == IN ? hi : bv - hi;             // rounded to bf16 below: bf16(b), bf16(b - hi)
+          }
           if (k >= K) return 0.0f;
           if (l < L) return n < U ? m->kernels[e * (L + 2) + l][(size_t)k * U + n] : 0.0f;
           if (n < O) return m->kernels[e * (L + 2) + L][(size_t)k * O + n];
@@ -862,8 +875,11 @@ static int do_rollout_score(simba_planner_t* p, const float* states, const float
   prm.row_return = row_return; prm.row_costmask = row_costmask; prm.row_costsum = row_costsum;
   prm.tc_tiles_per_cta = p->tiles_per_cta;
   prm.pdl = pdl ? 1 : 0;
-  if (const char* tlp = getenv("SIMBA_TC_TIMELINE_PTR"))   // debug builds only (tools/tc_timeline.py)
-    prm.traj_out = reinterpret_cast<float*>(strtoull(tlp, nullptr, 10));
+#ifdef SIMBA_TC_TIMELINE
+  // debug builds only (tools/tc_timeline.py): a scratch buffer for the kernels' clock64 stamps
+  if (const char* tlp = getenv("SIMBA_TC_TIMELINE_PTR"))
+    prm.timeline = reinterpret_cast<long long*>(strtoull(tlp, nullptr, 10));
+#endif
   if (p->cfg.precision == SIMBA_PREC_BF16_TC) {
     if (p->model->cfg.units <= 128) {
       CUDA_TRY(launch_rollout_tc(prm, prm.n_tiles, (cudaStream_t)stream));

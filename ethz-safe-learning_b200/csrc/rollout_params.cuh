@@ -59,6 +59,7 @@ struct RolloutParams {
   float* mu_out;              // [rows, O] or null (with var_out; sample_out optional)
   float* var_out;
   float* sample_out;
+  long long* timeline;        // clock64 stamps of CTA 0 (-DSIMBA_TC_TIMELINE builds only, else null)
 };
 
 size_t rollout_f32_smem_bytes(const RolloutParams& prm);

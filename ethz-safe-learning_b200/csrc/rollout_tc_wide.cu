@@ -31,12 +31,12 @@
 namespace simba {
 
 // Debug timeline (compile with -DSIMBA_TC_TIMELINE): epilogue thread 0 and the last epilogue warp's
-// lane 0 of CTA 0 stamp clock64() at phase boundaries into prm.traj_out (tools/tc_timeline.py c5).
+// lane 0 of CTA 0 stamp clock64() at phase boundaries into prm.timeline (tools/tc_timeline.py c5).
 #ifdef SIMBA_TC_TIMELINE
 #define TLW(ev)                                                                                  \
   do {                                                                                           \
     if (tl_who >= 0 && blockIdx.x == 0)                                                          \
-      reinterpret_cast<long long*>(prm.traj_out)[(tl_who * 64 + tl_t) * 64 + (ev)] = clock64();  \
+      prm.timeline[(tl_who * 64 + tl_t) * 64 + (ev)] = clock64();  \
   } while (0)
 #else
 #define TLW(ev) do { } while (0)

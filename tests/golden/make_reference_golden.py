@@ -139,7 +139,7 @@ def main():
             plan_fixture(out, 'penalty_break', c, 'penalty', z, eps, zf, stddev_threshold=0.9)
             plan_fixture(out, 'reward_mean_prop', c, 'reward', z, eps, zf, sampling_propagation=False)
             plan_fixture(out, 'penalty_vases', c, 'penalty', z, eps, zf,
-                         scorer_config=dict(constrain_vases=True, constrain_indicator=False))
+                         scorer_config=dict(constrain_vases=True))
         path = os.path.join(ROOT, 'tests', 'golden', 'reference_%s_plan.npz' % cfg)
         np.savez_compressed(path, **out)
         print("wrote %s: %d arrays" % (path, len(out)))

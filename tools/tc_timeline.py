@@ -22,8 +22,8 @@ st = torch.from_numpy(np.ascontiguousarray(synthetic.make_state(c['sensors'], 5,
 acts = torch.empty((S, N, H, A), device='cuda').uniform_(-1, 1)
 ret = torch.empty((S, P_, N), device='cuda'); msk = torch.empty((S, P_, N), dtype=torch.int64, device='cuda')
 csum = torch.empty((S, P_, N), device='cuda')
-# the timeline build stamps into prm.traj_out; simba_rollout_score leaves it null, so use the env hook
-tl = torch.zeros((2, 64, 64), dtype=torch.int64, device='cuda')
+# the timeline build stamps into prm.timeline, handed in through the env hook of the debug build
+tl = torch.zeros((3, 64, 64), dtype=torch.int64, device='cuda')
 os.environ['SIMBA_TC_TIMELINE_PTR'] = str(tl.data_ptr())
 p = lambda t: C.c_void_p(t.data_ptr())
 for it in range(3):
@@ -31,20 +31,36 @@ for it in range(3):
 torch.cuda.synchronize()
 t = tl.cpu().numpy()
 L = c['L']
-for who, name in ((0, 'issuer (warp 0)'), (1, 'last warp of tile')):
-    print("==", name)
-    rows = []
-    for step in range(2, H - 1):
+if wl == 'c5':                     # rollout_tc_wide.cu keeps the round-1 event layout
+    for who, name in ((0, 'epilogue warp 0'), (1, 'last warp of tile')):
+        print("==", name)
+        for step in range(2, min(H - 1, 8)):
+            ev = t[who, step]
+            base = ev[0]
+            line = ["step %2d" % step]
+            for l in range(L):
+                line.append("L%d wait->%5d epi->%5d publish->%5d |" % (l, ev[1 + 4 * l] - base, ev[2 + 4 * l] - base, ev[3 + 4 * l] - base))
+            line.append("head wait->%5d pass->%5d publish->%5d score->%5d  total %5d" % (
+                ev[40] - base, ev[41] - base, ev[42] - base, ev[43] - base, t[who, step + 1][0] - base))
+            print(' '.join(line))
+    sys.exit(0)
+# rollout_tc.cu: epilogue warps stamp 0 (step start), per hidden layer l: 1+4l accumulator ready, 2+4l drained,
+# 3+4l A slice published, 4+4l noise block done; 40 head accumulator ready, 41 head pass done, 42 published,
+# 43 scored. The issuer warp of tile 0 (who = 2) stamps 2*layer (A ready seen) and 2*layer+1 (layer committed).
+for who, name in ((0, 'epilogue warp 0 of tile 0'), (1, 'last epilogue warp of tile 0')):
+    print("==", name, "(cycles since the step's start)")
+    for step in range(2, min(H - 1, 8)):
         ev = t[who, step]
         base = ev[0]
         line = ["step %2d" % step]
         for l in range(L):
-            line.append("L%d wait->%5d epi->%5d sync+issue->%5d |" % (l, ev[1 + 4 * l] - base, ev[2 + 4 * l] - base, ev[3 + 4 * l] - base))
-        line.append("head wait->%5d pass->%5d sync+issue->%5d score->%5d  total %5d" % (
+            line.append("L%d acc->%5d drained->%5d published->%5d noise->%5d |" % (
+                l, ev[1 + 4 * l] - base, ev[2 + 4 * l] - base, ev[3 + 4 * l] - base, ev[4 + 4 * l] - base))
+        line.append("head acc->%5d pass->%5d published->%5d scored->%5d  total %5d" % (
             ev[40] - base, ev[41] - base, ev[42] - base, ev[43] - base, t[who, step + 1][0] - base))
-        line.append("| issue detail (st_wait, barrier) per layer: " + ' '.join(
-            "%d:(%d,%d)" % (l, ev[48 + l] - base, ev[54 + l] - base) for l in range(L + 1)))
-        line.append("| head detail: ld_wait->%d state_st->%d before_st_wait->%d after->%d" % tuple(
-            ev[k] - base for k in (44, 45, 46, 47)))
-        rows.append(' '.join(line))
-    print('\n'.join(rows[:6]))
+        print(' '.join(line))
+print("== issuer warp of tile 0 (cycles since epilogue warp 0's step start; layer: A-ready seen -> committed)")
+for step in range(2, min(H - 1, 8)):
+    base = t[0, step][0]
+    ev = t[2, step]
+    print("step %2d " % step + ' | '.join("L%d %5d -> %5d" % (l, ev[2 * l] - base, ev[2 * l + 1] - base) for l in range(L + 1)))
