@@ -220,14 +220,19 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
             named_bar_sync<kTileThreads + 32>(kBarA + j);     // every epilogue warp's slice of this layer's A is in TMEM
             tc_fence_after();
             TL(2 * layer);
-            if (lane == 0) {
-              const int ksteps = (layer == 0) ? 4 : 8;        // K = 64 or 128, UMMA_K = 16
+            if (elect_one()) {                                // ptxas must KNOW one lane is active: with a plain
+                                                              // lane test every UTCHMMA gets an operand waterfall loop
+              // descriptor arithmetic hoisted out of the K loop: one add per MMA on the 14-bit address field
               const uint32_t woff = (layer == 0) ? 0u : (uint32_t)(kAtomBytes + (layer - 1) * 2 * kAtomBytes);
-              const uint32_t b_base = smem_u32(w_smem + woff);
-              for (int k = 0; k < ksteps; ++k) {
-                const uint32_t koff = (uint32_t)(k >> 2) * kAtomBytes + (uint32_t)(k & 3) * 32;
-                umma_bf16_ts(d_tmem, a_tmem + (uint32_t)k * 8,                   // 16 bf16 = 8 columns
-                             umma_desc_sw128(b_base + koff), kIdesc, k > 0 ? 1u : 0u);
+              const uint64_t b0 = umma_desc_sw128(smem_u32(w_smem + woff));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)                     // K = 64 (layer 0) ...
+                umma_bf16_ts(d_tmem, a_tmem + (uint32_t)k * 8, b0 + (uint64_t)((k * 32) >> 4), kIdesc, k > 0 ? 1u : 0u);
+              if (layer > 0) {
+#pragma unroll
+                for (int k = 4; k < 8; ++k)                   // ... or 128; UMMA_K = 16 = 8 TMEM columns of bf16 pairs
+                  umma_bf16_ts(d_tmem, a_tmem + (uint32_t)k * 8, b0 + (uint64_t)((kAtomBytes + (k - 4) * 32) >> 4),
+                               kIdesc, 1u);
               }
               // + bias: ones[128 x 16] * biasK[16 x 128] (bf16 hi + lo rows), both operands from SMEM
               if (layer > 0 || !l0_pad_bias)

@@ -178,6 +178,17 @@ __device__ __forceinline__ void named_bar_sync(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kThreads) : "memory");
 }
 
+// true in exactly one (the lowest) lane of the converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // producer side of a named barrier: counts this warp in without waiting (pairs with bar.sync)
 template <int kThreads>
 __device__ __forceinline__ void named_bar_arrive(int id) {
