@@ -146,14 +146,16 @@ __device__ __forceinline__ void head_chunk_tail(const HeadCtx& c, const AStore& 
     }
   }
   if (write_next) {
-    const float4 a0 = *reinterpret_cast<const float4*>(c.scale_smem + oc);
-    const float4 a1 = *reinterpret_cast<const float4*>(c.scale_smem + oc + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(c.scale_smem + 64 + oc);
-    const float4 b1 = *reinterpret_cast<const float4*>(c.scale_smem + 64 + oc + 4);
-    astore.store8(oc, pack_bf16(fmaf(sv[0], a0.x, b0.x), fmaf(sv[1], a0.y, b0.y)),
-                  pack_bf16(fmaf(sv[2], a0.z, b0.z), fmaf(sv[3], a0.w, b0.w)),
-                  pack_bf16(fmaf(sv[4], a1.x, b1.x), fmaf(sv[5], a1.y, b1.y)),
-                  pack_bf16(fmaf(sv[6], a1.z, b1.z), fmaf(sv[7], a1.w, b1.w)));
+    const ulonglong2 a0 = *reinterpret_cast<const ulonglong2*>(c.scale_smem + oc);
+    const ulonglong2 a1 = *reinterpret_cast<const ulonglong2*>(c.scale_smem + oc + 4);
+    const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(c.scale_smem + 64 + oc);
+    const ulonglong2 b1 = *reinterpret_cast<const ulonglong2*>(c.scale_smem + 64 + oc + 4);
+    float x[8];
+    f2_unpack(f2_fma(f2_pack(sv[0], sv[1]), a0.x, b0.x), x[0], x[1]);
+    f2_unpack(f2_fma(f2_pack(sv[2], sv[3]), a0.y, b0.y), x[2], x[3]);
+    f2_unpack(f2_fma(f2_pack(sv[4], sv[5]), a1.x, b1.x), x[4], x[5]);
+    f2_unpack(f2_fma(f2_pack(sv[6], sv[7]), a1.y, b1.y), x[6], x[7]);
+    astore.store8(oc, pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
   }
 }
 
@@ -228,11 +230,27 @@ __device__ __forceinline__ void head_step_pass(const HeadCtx& c, const Noise& no
     if (kSample) {
       const uint4 nz = noise.get4(ch);
       const uint32_t nw[4] = {nz.x, nz.y, nz.z, nz.w};
+      // two outputs per instruction wherever the op exists as fp32x2 (the MUFU ops and the clamp do not)
+      const f32x2 kLog2e = f2_pack(1.4426950408889634f, 1.4426950408889634f), kOne = f2_pack(1.0f, 1.0f);
+      const f32x2 kLn2 = f2_pack(0.6931471805599453f, 0.6931471805599453f), kFloor = f2_pack(1e-4f, 1e-4f);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float eps = (q & 1) ? __uint_as_float(nw[q >> 1] & 0xffff0000u) : __uint_as_float(nw[q >> 1] << 16);
-        const float d = fmaf(head_stddev(__uint_as_float(vv[cur][q])), eps, __uint_as_float(vm[cur][q]));
-        sv[q] = __uint_as_float(st[cur][q]) + d;
+      for (int q = 0; q < 8; q += 2) {
+        float e0, e1, l0, l1, s0, s1;
+        // sqrt(softplus(x) + 1e-4), see head_stddev
+        f2_unpack(f2_mul(f2_pack(fminf(__uint_as_float(vv[cur][q]), 80.0f), fminf(__uint_as_float(vv[cur][q + 1]), 80.0f)),
+                         kLog2e), e0, e1);
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(e0));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(e1));
+        f2_unpack(f2_add(f2_pack(e0, e1), kOne), l0, l1);
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(l0));
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l1) : "f"(l1));
+        f2_unpack(f2_fma(f2_pack(l0, l1), kLn2, kFloor), s0, s1);
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(s0));
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(s1));
+        const f32x2 eps = f2_pack(__uint_as_float(nw[q >> 1] << 16), __uint_as_float(nw[q >> 1] & 0xffff0000u));
+        const f32x2 mu = f2_pack(__uint_as_float(vm[cur][q]), __uint_as_float(vm[cur][q + 1]));
+        const f32x2 old = f2_pack(__uint_as_float(st[cur][q]), __uint_as_float(st[cur][q + 1]));
+        f2_unpack(f2_add(old, f2_fma(f2_pack(s0, s1), eps, mu)), sv[q], sv[q + 1]);
       }
     } else {
 #pragma unroll
