@@ -580,6 +580,7 @@ struct simba_planner {
   Tile* d_tiles = nullptr;
   int tile_rows = 0;
   int tiles_per_cta = 1;
+
   bool use_pdl = false;        // programmatic dependent launch between rollout and fused update kernels
   bool fused_update = false;   // one rank, N <= 1024: reduce+select+refit(+next sample | finalize) in one kernel
   int c_max = -1;
@@ -722,6 +723,7 @@ extern "C" int simba_planner_create(simba_model_t* model, const simba_planner_co
     p->tiles_per_cta = 2;
     build_tiles(p->geom, p->tile_rows, p->tiles, 2);
   }
+
   p->fused_update = cfg->world_size == 1 && cfg->n_samples <= 1024 && getenv("SIMBA_B200_NO_FUSE") == nullptr;
   p->use_pdl = p->fused_update && cfg->precision == SIMBA_PREC_BF16_TC && getenv("SIMBA_B200_NO_PDL") == nullptr;
   p->c_max = beta_count_threshold(cfg->particles, cfg->posterior_mean_threshold, cfg->prior_mu,
