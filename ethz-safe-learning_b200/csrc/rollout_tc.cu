@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
   // Throughput variant: the step's noise and the per-row running objective are parked in shared
   // memory to free registers. Latency variant (one tile): they stay in registers.
   constexpr bool kPark = NTILES > 1;
-  constexpr int kBarAcc = 2, kBarA = 2 + NTILES, kBarScore = 2 + 2 * NTILES;   // named barrier ids (+ tile)
+  constexpr int kBarAcc = 2, kBarA = 2 + NTILES, kBarPart = 2 + 2 * NTILES, kBarFree = 2 + 3 * NTILES;   // ids (+ tile)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const RowGeom& g = prm.g;
   const int L = prm.L;
@@ -130,12 +130,9 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
   const int nparts = 1 + prm.scorer.n_constraints;                         // goal + constrained lidars
   float* part_smem = pen_smem + kHeadParts * 64;                           // [NTILES][Q][nparts][128]
   uint4* noise_smem = reinterpret_cast<uint4*>(part_smem + NTILES * Q * nparts * 128);   // [NB][threads]
-  // running objective of every rollout row (RowScore fields, field-major): only one of the Q threads of a
-  // row scores, and only once per step, so the words live here instead of in registers
-  uint32_t* rs_smem = reinterpret_cast<uint32_t*>(noise_smem + (kPark ? NB * kEpiThreads : 0));   // [8][NTILES*128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(rs_smem + (kPark ? 8 * NTILES * 128 : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(noise_smem + (kPark ? NB * kEpiThreads : 0));
   // bars[0] = weights landed; bars[1 + j] = MMAs of tile j committed. Named barriers: 0 = CTA, 1 = all
-  // epilogue threads, 2 + j = "accumulator ready" of tile j, 2 + NTILES + j = "A ready", 2 + 2 NTILES + j = scoring
+  // epilogue threads, 2 + j = "accumulator ready" of tile j, 2 + NTILES + j = "A ready"
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + NTILES);
   TileInfo* tinfo = reinterpret_cast<TileInfo*>(tmem_slot + 2);
   uint64_t* seed_sh = reinterpret_cast<uint64_t*>(tinfo + NTILES);
@@ -184,7 +181,52 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
     if (tinfo[j].valid) { any_valid = true; member = tinfo[j].member; }
 
   if (any_valid) {
-    if (warp >= kEpiWarps) {
+    if (warp >= kEpiWarps + NTILES) {
+      // ====================== scorer warp of tile j: the per-row objective, off everybody's critical path ======
+      // (mpc_policy.py:30-37 / safe_cem_mpc.py:82-93 on safety_gym.py:110-166). Lane i owns rows i, i + 32,
+      // i + 64, i + 96 of the tile. After every head pass the epilogue warps bar.arrive on "partials
+      // published"; this warp bar.sync's on it, combines the Q partial lidar minima of each row into the
+      // goal distance / cost of s_{t+1}, advances the row's objective, and bar.arrive's on "partials free",
+      // which the epilogue warps pass (normally without waiting: it is L layers old by then) before their
+      // next head pass overwrites the exchange buffer.
+      const int j = warp - kEpiWarps - NTILES;
+      const TileInfo tis = tinfo[j];
+      if (tis.valid) {
+        const simba_scorer_t& sc = prm.scorer;
+        const bool done_first = objective_done_first(prm.objective);
+        RowScore rs[4];
+        int64_t out_slot[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = lane + 32 * i;
+          rs[i].cum = 0.0f; rs[i].costsum = 0.0f; rs[i].cmask = 0ull; rs[i].done = false;
+          rs[i].dist = 0.0f; rs[i].cost = 0.0f;
+          out_slot[i] = row < tis.count ? decode_row(g, tis.member, tis.k0 + row).out : -1;
+        }
+        const float* part_tile = part_smem + (j * Q * nparts) * 128;       // [Q][nparts][128 rows]
+        for (int ts = -1; ts < H; ++ts) {                                  // ts = -1: distance / cost of s_0
+          named_bar_sync<kTileThreads + 32>(kBarPart + j);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float nd, nc;
+            head_combine<Q>(sc, part_tile + lane + 32 * i, nparts, nd, nc);
+            if (ts < 0) { rs[i].dist = nd; rs[i].cost = nc; }
+            else head_score_step(rs[i], sc, done_first, ts, nd, nc);
+          }
+          if (ts + 1 < H) named_bar_arrive<kTileThreads + 32>(kBarFree + j);
+        }
+        if (prm.row_return != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (out_slot[i] >= 0) {
+              prm.row_return[out_slot[i]] = rs[i].cum;
+              prm.row_costmask[out_slot[i]] = rs[i].cmask;
+              prm.row_costsum[out_slot[i]] = rs[i].costsum;
+            }
+          }
+        }
+      }
+    } else if (warp >= kEpiWarps) {
       // ====================== MMA issuer warp of tile j (lane 0 issues; the warp stays converged) ==============
       const int j = warp - kEpiWarps;
       if (tinfo[j].valid) {
@@ -275,7 +317,6 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
         const uint32_t t_acc = lane_base + (uint32_t)j * 128;
         const uint32_t t_a = lane_base + (uint32_t)(NTILES * 192 + j * 64);   // this row's A-operand columns
         const float* act_ptr = prm.actions + ((int64_t)id.s * g.N + id.i_global) * prm.action_stride;
-        const bool done_first = objective_done_first(prm.objective);
         const simba_scorer_t& sc = prm.scorer;
 
         HeadCtx hc;
@@ -288,7 +329,6 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
         hc.scale_smem = scale_smem;
         hc.pen_smem = pen_smem;
         hc.part = part_smem + ((j * Q + cgp) * nparts) * 128 + r;              // [nparts] stride 128
-        const float* part_row = part_smem + (j * Q * nparts) * 128 + r;        // group 0 base of this row
         const AStoreTmem astore{t_a};
         const float* s0_ptr = prm.states + (prm.state_per_row ? id.r_global : (int64_t)id.s) * prm.state_stride;
 
@@ -357,33 +397,11 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
           noise.put4(b, z);
         };
 
-        constexpr int kRsStride = NTILES * 128;
-        uint32_t* my_rs = rs_smem + j * 128 + r;            // cum, costsum, cmask lo / hi, dist, cost, done, out
-        RowScore rs;                                        // the same in registers (latency variant)
-        rs.cum = 0.0f; rs.costsum = 0.0f; rs.cmask = 0ull; rs.done = false;
-        rs.dist = 0.0f; rs.cost = 0.0f;
-
         prefetch_actions(0);
         head_first_pass<OW>(hc, astore, s0_ptr, row_ok, act_pf);
         prefetch_actions(1);
         publish_a();                                        // layer-0 input of step 0
-        named_bar_sync<kTileThreads>(kBarScore + j);        // partial minima of s_0 visible to the scorers
-        if (cgp == 0) {
-          float d0, c0;
-          head_combine<Q>(sc, part_row, nparts, d0, c0);
-          if constexpr (kPark) {
-            my_rs[0] = 0u; my_rs[kRsStride] = 0u; my_rs[2 * kRsStride] = 0u; my_rs[3 * kRsStride] = 0u;
-            my_rs[4 * kRsStride] = __float_as_uint(d0);
-            my_rs[5 * kRsStride] = __float_as_uint(c0);
-            my_rs[6 * kRsStride] = 0u;
-            my_rs[7 * kRsStride] = (uint32_t)id.out;        // output slot of this row, needed again at the end
-          } else {
-            rs.dist = d0;
-            rs.cost = c0;
-          }
-        }
-        // (the partials are next written after the tile has gone through L + 1 more A-ready rounds,
-        //  each of which needs an arrive of the group-0 warps, which they give only after combine())
+        named_bar_arrive<kTileThreads + 32>(kBarPart + j);  // partial minima of s_0 published (scorer warp)
 
         for (int t = 0; t < H; ++t) {
 #ifdef SIMBA_TC_TIMELINE
@@ -425,50 +443,14 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
 
           // ---- Gaussian heads + state update + next input + partial minima (one fused pass) --------
           wait_accumulator();
+          named_bar_sync<kTileThreads + 32>(kBarFree + j);  // the scorer warp is done with the previous partials
           TL(40);
           if (prm.sampling_propagation) head_step_pass<OW, true>(hc, noise, astore, t + 1 < H);
           else head_step_pass<OW, false>(hc, noise, astore, t + 1 < H);
           TL(41);
-          // next step's layer 0 goes out first; then scoring of (s_t, s_{t+1}): safety_gym.py:110-166
-          if (t + 1 < H) publish_a();
-          else tmem_st_wait();
+          if (t + 1 < H) publish_a();                       // next step's layer 0 goes out
+          named_bar_arrive<kTileThreads + 32>(kBarPart + j);  // partial minima of s_{t+1} published (scorer warp)
           TL(42);
-          named_bar_sync<kTileThreads>(kBarScore + j);      // partial minima of s_{t+1} visible to the scorers
-          if (cgp == 0) {
-            float next_dist, next_cost;
-            head_combine<Q>(sc, part_row, nparts, next_dist, next_cost);
-            if constexpr (kPark) {
-              rs.cum = __uint_as_float(my_rs[0]);
-              rs.costsum = __uint_as_float(my_rs[kRsStride]);
-              rs.cmask = (uint64_t)my_rs[2 * kRsStride] | ((uint64_t)my_rs[3 * kRsStride] << 32);
-              rs.dist = __uint_as_float(my_rs[4 * kRsStride]);
-              rs.cost = __uint_as_float(my_rs[5 * kRsStride]);
-              rs.done = my_rs[6 * kRsStride] != 0u;
-            }
-            head_score_step(rs, sc, done_first, t, next_dist, next_cost);
-            if constexpr (kPark) {
-              my_rs[0] = __float_as_uint(rs.cum);
-              my_rs[kRsStride] = __float_as_uint(rs.costsum);
-              my_rs[2 * kRsStride] = (uint32_t)rs.cmask;
-              my_rs[3 * kRsStride] = (uint32_t)(rs.cmask >> 32);
-              my_rs[4 * kRsStride] = __float_as_uint(rs.dist);
-              my_rs[5 * kRsStride] = __float_as_uint(rs.cost);
-              my_rs[6 * kRsStride] = rs.done ? 1u : 0u;
-            }
-          }
-          TL(43);
-        }
-        if (cgp == 0 && row_ok && prm.row_return != nullptr) {
-          if constexpr (kPark) {
-            const uint32_t out_slot = my_rs[7 * kRsStride];
-            prm.row_return[out_slot] = __uint_as_float(my_rs[0]);
-            prm.row_costmask[out_slot] = (uint64_t)my_rs[2 * kRsStride] | ((uint64_t)my_rs[3 * kRsStride] << 32);
-            prm.row_costsum[out_slot] = __uint_as_float(my_rs[kRsStride]);
-          } else {
-            prm.row_return[id.out] = rs.cum;
-            prm.row_costmask[id.out] = rs.cmask;
-            prm.row_costsum[id.out] = rs.costsum;
-          }
         }
       }
     }
@@ -488,7 +470,6 @@ static size_t tc_smem_bytes(int L, int ntiles, int q, int nparts) {
   b += (size_t)ntiles * q * nparts * 128 * sizeof(float);          // partial minima exchange
   if (ntiles > 1) {                                                // parking areas of the two-tile variant
     b += (size_t)(64 / q / 8) * (ntiles * q * 128) * sizeof(uint4);      // bf16x2 noise of the current step
-    b += (size_t)8 * ntiles * 128 * sizeof(uint32_t);                    // per-row running objective
   }
   b += (1 + ntiles) * sizeof(uint64_t) + 2 * sizeof(uint32_t) + ntiles * sizeof(TileInfo) + sizeof(uint64_t);
   return b + 1024;                                                 // alignment slack
@@ -521,7 +502,7 @@ static cudaError_t launch_variant(const RolloutParams& prm, int n_tiles, cudaStr
   const int grid = (n_tiles + NTILES - 1) / NTILES;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(NTILES * Q * 128 + 32 * NTILES);             // epilogue warps + one issuer warp per tile
+  cfg.blockDim = dim3(NTILES * Q * 128 + 64 * NTILES);             // epilogue warps + an issuer and a scorer warp per tile
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
