@@ -75,12 +75,18 @@ struct NoiseSmem {                       // [block][thread] uint4: conflict-free
   uint4* base;
   __device__ __forceinline__ uint4 get4(int b) const { return base[b * kThreads]; }
   __device__ __forceinline__ void put4(int b, uint4 v) { base[b * kThreads] = v; }
+  __device__ __forceinline__ void put4_dyn(int b, uint4 v) { base[b * kThreads] = v; }
 };
 template <int NB>
 struct NoiseRegs {
   uint4 v[NB];
   __device__ __forceinline__ uint4 get4(int b) const { return v[b]; }
   __device__ __forceinline__ void put4(int b, uint4 x) { v[b] = x; }
+  __device__ __forceinline__ void put4_dyn(int b, uint4 x) {          // run-time index without local memory
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+      if (i == b) v[i] = x;
+  }
 };
 
 // A operand in tensor memory: K elements [k0, k0 + 8) of this thread's row = 4 columns of bf16 pairs
@@ -130,7 +136,9 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
   const int nparts = 1 + prm.scorer.n_constraints;                         // goal + constrained lidars
   float* part_smem = pen_smem + kHeadParts * 64;                           // [NTILES][Q][nparts][128]
   uint4* noise_smem = reinterpret_cast<uint4*>(part_smem + NTILES * Q * nparts * 128);   // [NB][threads]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(noise_smem + (kPark ? NB * kEpiThreads : 0));
+  // running objective of every rollout row (RowScore fields, field-major), kept by the tile's scorer warp
+  uint32_t* rs_smem = reinterpret_cast<uint32_t*>(noise_smem + (kPark ? NB * kEpiThreads : 0));   // [NTILES][8][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rs_smem + NTILES * 8 * 128);
   // bars[0] = weights landed; bars[1 + j] = MMAs of tile j committed. Named barriers: 0 = CTA, 1 = all
   // epilogue threads, 2 + j = "accumulator ready" of tile j, 2 + NTILES + j = "A ready"
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + NTILES);
@@ -194,34 +202,57 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
       if (tis.valid) {
         const simba_scorer_t& sc = prm.scorer;
         const bool done_first = objective_done_first(prm.objective);
-        RowScore rs[4];
-        int64_t out_slot[4];
-#pragma unroll
+        // the objective of the lane's four rows is parked in shared memory (field-major), so the row
+        // loop stays rolled: this warp is never on the critical path and the kernel already exceeds the
+        // instruction cache
+        uint32_t* my_rs = rs_smem + j * 8 * 128 + lane;                    // [8 fields][128 rows]
+        const float* part_tile = part_smem + (j * Q * nparts) * 128;       // [Q][nparts][128 rows]
+#pragma unroll 1
         for (int i = 0; i < 4; ++i) {
           const int row = lane + 32 * i;
-          rs[i].cum = 0.0f; rs[i].costsum = 0.0f; rs[i].cmask = 0ull; rs[i].done = false;
-          rs[i].dist = 0.0f; rs[i].cost = 0.0f;
-          out_slot[i] = row < tis.count ? decode_row(g, tis.member, tis.k0 + row).out : -1;
+#pragma unroll
+          for (int f = 0; f < 7; ++f) my_rs[f * 128 + 32 * i] = 0u;
+          my_rs[7 * 128 + 32 * i] = row < tis.count ? (uint32_t)decode_row(g, tis.member, tis.k0 + row).out : 0xffffffffu;
         }
-        const float* part_tile = part_smem + (j * Q * nparts) * 128;       // [Q][nparts][128 rows]
         for (int ts = -1; ts < H; ++ts) {                                  // ts = -1: distance / cost of s_0
           named_bar_sync<kTileThreads + 32>(kBarPart + j);
-#pragma unroll
+#pragma unroll 1
           for (int i = 0; i < 4; ++i) {
+            uint32_t* q = my_rs + 32 * i;
             float nd, nc;
             head_combine<Q>(sc, part_tile + lane + 32 * i, nparts, nd, nc);
-            if (ts < 0) { rs[i].dist = nd; rs[i].cost = nc; }
-            else head_score_step(rs[i], sc, done_first, ts, nd, nc);
+            if (ts < 0) {
+              q[4 * 128] = __float_as_uint(nd);
+              q[5 * 128] = __float_as_uint(nc);
+            } else {
+              RowScore rs;
+              rs.cum = __uint_as_float(q[0]);
+              rs.costsum = __uint_as_float(q[128]);
+              rs.cmask = (uint64_t)q[2 * 128] | ((uint64_t)q[3 * 128] << 32);
+              rs.dist = __uint_as_float(q[4 * 128]);
+              rs.cost = __uint_as_float(q[5 * 128]);
+              rs.done = q[6 * 128] != 0u;
+              head_score_step(rs, sc, done_first, ts, nd, nc);
+              q[0] = __float_as_uint(rs.cum);
+              q[128] = __float_as_uint(rs.costsum);
+              q[2 * 128] = (uint32_t)rs.cmask;
+              q[3 * 128] = (uint32_t)(rs.cmask >> 32);
+              q[4 * 128] = __float_as_uint(rs.dist);
+              q[5 * 128] = __float_as_uint(rs.cost);
+              q[6 * 128] = rs.done ? 1u : 0u;
+            }
           }
           if (ts + 1 < H) named_bar_arrive<kTileThreads + 32>(kBarFree + j);
         }
         if (prm.row_return != nullptr) {
-#pragma unroll
+#pragma unroll 1
           for (int i = 0; i < 4; ++i) {
-            if (out_slot[i] >= 0) {
-              prm.row_return[out_slot[i]] = rs[i].cum;
-              prm.row_costmask[out_slot[i]] = rs[i].cmask;
-              prm.row_costsum[out_slot[i]] = rs[i].costsum;
+            const uint32_t* q = my_rs + 32 * i;
+            const uint32_t slot = q[7 * 128];
+            if (slot != 0xffffffffu) {
+              prm.row_return[slot] = __uint_as_float(q[0]);
+              prm.row_costmask[slot] = (uint64_t)q[2 * 128] | ((uint64_t)q[3 * 128] << 32);
+              prm.row_costsum[slot] = __uint_as_float(q[128]);
             }
           }
         }
@@ -374,16 +405,19 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
         const float* eps_row = prm.eps == nullptr ? nullptr
             : prm.eps + ((int64_t)id.s * H * ((int64_t)g.P * g.N) + id.r_global) * O;
         const int64_t eps_step = (int64_t)g.P * g.N * O;
-        auto make_noise = [&](int b, int t) {               // Philox block b in [0, NB) of step t
+        // One Philox block (8 draws) of step t; b may be a run-time value (one call site per layer keeps the
+        // layer loop small: the kernel is far larger than the instruction cache).
+        const uint64_t seed64 = *seed_sh;
+        const uint2 key = make_uint2((uint32_t)seed64, (uint32_t)(seed64 >> 32));
+        const uint32_t c2_base = (uint32_t)prm.iteration << 16;
+        auto make_noise = [&](int b, int t) {
           const int o0 = hc.o_base + b * 8;
-          if (o0 >= O) return;                              // warp-uniform
+          if (o0 >= O) return;                              // warp-uniform: nothing to draw
           uint4 z;
           if (eps_row != nullptr) {
             z = external_noise8_bf16(eps_row + t * eps_step, o0, O);
           } else {
-            const uint64_t seed = *seed_sh;
-            z = philox_noise8_bf16(make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), (uint32_t)(o0 >> 3), row32,
-                                   (uint32_t)t | ((uint32_t)prm.iteration << 16), c3_noise);
+            z = philox_noise8_bf16(key, (uint32_t)(o0 >> 3), row32, (uint32_t)t | c2_base, c3_noise);
             if (o0 + 8 > O) {                               // padded outputs draw nothing (their delta is 0)
               uint32_t w[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
@@ -394,9 +428,8 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
               z = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
-          noise.put4(b, z);
+          noise.put4_dyn(b, z);
         };
-
         prefetch_actions(0);
         head_first_pass<OW>(hc, astore, s0_ptr, row_ok, act_pf);
         prefetch_actions(1);
@@ -433,10 +466,10 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
             publish_a();
             TL(3 + l * 4);
             if (prm.sampling_propagation) {
-              // spread the NB Philox blocks over the hidden layers (the last layer takes the rest)
-#pragma unroll
-              for (int b = 0; b < NB; ++b)
-                if ((b < L - 1 ? b : L - 1) == l) make_noise(b, t);
+              // the NB Philox blocks of the step, one per hidden layer (the last layer takes the rest)
+              if (l < NB) make_noise(l, t);
+              if (l == L - 1)
+                for (int b = L; b < NB; ++b) make_noise(b, t);
             }
             TL(4 + l * 4);
           }
@@ -468,9 +501,9 @@ static size_t tc_smem_bytes(int L, int ntiles, int q, int nparts) {
   b += 128 * sizeof(float);                                        // scaler
   b += kHeadParts * 64 * sizeof(float);                            // slice penalty table
   b += (size_t)ntiles * q * nparts * 128 * sizeof(float);          // partial minima exchange
-  if (ntiles > 1) {                                                // parking areas of the two-tile variant
+  if (ntiles > 1)                                                  // parking area of the two-tile variant:
     b += (size_t)(64 / q / 8) * (ntiles * q * 128) * sizeof(uint4);      // bf16x2 noise of the current step
-  }
+  b += (size_t)8 * ntiles * 128 * sizeof(uint32_t);                      // per-row running objective
   b += (1 + ntiles) * sizeof(uint64_t) + 2 * sizeof(uint32_t) + ntiles * sizeof(TileInfo) + sizeof(uint64_t);
   return b + 1024;                                                 // alignment slack
 }
