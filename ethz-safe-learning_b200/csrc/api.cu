@@ -66,6 +66,8 @@ extern "C" int simba_device_check(void) {
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+constexpr float kLog2e = 1.4426950408889634f;
+
 static float bf16_to_f32(uint16_t h) {
   const uint32_t u = (uint32_t)h << 16;
   float f;
@@ -309,7 +311,9 @@ extern "C" int simba_model_commit(simba_model_t* m) {
           if (k >= K) return 0.0f;
           if (l < L) return n < U ? m->kernels[e * (L + 2) + l][(size_t)k * U + n] : 0.0f;
           if (n < O) return m->kernels[e * (L + 2) + L][(size_t)k * O + n];
-          if (n >= 64 && n < 64 + O) return m->kernels[e * (L + 2) + L + 1][(size_t)k * O + (n - 64)];
+          // the raw-variance head is pre-scaled by log2(e): the kernels evaluate softplus as
+          // ln2 * lg2(1 + ex2(x log2 e)) and get x log2 e straight out of the GEMM
+          if (n >= 64 && n < 64 + O) return kLog2e * m->kernels[e * (L + 2) + L + 1][(size_t)k * O + (n - 64)];
           return 0.0f;
         };
         const int Kp = l == 0 ? IN : 128;
@@ -334,7 +338,7 @@ extern "C" int simba_model_commit(simba_model_t* m) {
         for (int n = 0; n < U; ++n) bt[((size_t)e * (L + 1) + l) * 128 + n] = m->biases[e * (L + 2) + l][n];
       for (int n = 0; n < O; ++n) {
         bt[((size_t)e * (L + 1) + L) * 128 + n] = m->biases[e * (L + 2) + L][n];
-        bt[((size_t)e * (L + 1) + L) * 128 + 64 + n] = m->biases[e * (L + 2) + L + 1][n];
+        bt[((size_t)e * (L + 1) + L) * 128 + 64 + n] = kLog2e * m->biases[e * (L + 2) + L + 1][n];   // (see above)
       }
     }
     if (!m->d_bias_tc) CUDA_TRY(cudaMalloc(&m->d_bias_tc, bt.size() * sizeof(float)));
@@ -395,10 +399,11 @@ extern "C" int simba_model_commit(simba_model_t* m) {
             return 0;                                      // padded hidden unit: weights and bias 0
           }
           const int width = l < L ? U : O;
-          if (k < K) return f32_to_bf16_rne(m->kernels[e * (L + 2) + layer][(size_t)k * width + col]);
+          const float pre = layer == L + 1 ? kLog2e : 1.0f;   // raw-variance head pre-scaled by log2(e)
+          if (k < K) return f32_to_bf16_rne(pre * m->kernels[e * (L + 2) + layer][(size_t)k * width + col]);
           if (k == KB || k == KB + 1) {
             uint16_t hi, lo;
-            split_bias(m->biases[e * (L + 2) + layer][col], hi, lo);
+            split_bias(pre * m->biases[e * (L + 2) + layer][col], hi, lo);
             return k == KB ? hi : lo;
           }
           return 0;

@@ -110,12 +110,14 @@ struct HeadCtx {
 };
 
 // sqrt(softplus(x) + 1e-4) on the MUFU path (mlp_ensemble.py:30, :192): ln(1 + e^x) =
-// lg2(1 + ex2(x log2 e)) ln 2. Flush-to-zero ex2 (e^x < 2^-126 adds nothing to 1), the clamp keeps
-// e^x finite so that large x gives softplus(x) = x. The rounding of 1 + e costs <= 6e-8 absolute,
-// i.e. <= 6e-4 relative to the variance because of its 1e-4 floor — far inside the bf16 tolerance.
-__device__ __forceinline__ float head_stddev(float x) {
+// ln 2 * lg2(1 + ex2(x log2 e)). The raw-variance head's weights and bias are packed pre-scaled by
+// log2(e) (simba_model_commit), so the accumulator holds x log2 e. Flush-to-zero ex2 (e^x < 2^-126
+// adds nothing to 1), the clamp keeps e^x finite so that large x gives softplus(x) = x. The rounding
+// of 1 + e costs <= 6e-8 absolute, i.e. <= 6e-4 relative to the variance because of its 1e-4 floor —
+// far inside the bf16 tolerance.
+__device__ __forceinline__ float head_stddev(float x_log2e) {
   float e, l, sd;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(x, 80.0f) * 1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(x_log2e, 120.0f)));
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sd) : "f"(fmaf(l, 0.6931471805599453f, 1e-4f)));
   return sd;
@@ -231,16 +233,14 @@ __device__ __forceinline__ void head_step_pass(const HeadCtx& c, const Noise& no
       const uint4 nz = noise.get4(ch);
       const uint32_t nw[4] = {nz.x, nz.y, nz.z, nz.w};
       // two outputs per instruction wherever the op exists as fp32x2 (the MUFU ops and the clamp do not)
-      const f32x2 kLog2e = f2_pack(1.4426950408889634f, 1.4426950408889634f), kOne = f2_pack(1.0f, 1.0f);
+      const f32x2 kOne = f2_pack(1.0f, 1.0f);
       const f32x2 kLn2 = f2_pack(0.6931471805599453f, 0.6931471805599453f), kFloor = f2_pack(1e-4f, 1e-4f);
 #pragma unroll
       for (int q = 0; q < 8; q += 2) {
         float e0, e1, l0, l1, s0, s1;
-        // sqrt(softplus(x) + 1e-4), see head_stddev
-        f2_unpack(f2_mul(f2_pack(fminf(__uint_as_float(vv[cur][q]), 80.0f), fminf(__uint_as_float(vv[cur][q + 1]), 80.0f)),
-                         kLog2e), e0, e1);
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(e0));
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(e1));
+        // sqrt(softplus(x) + 1e-4), see head_stddev; the accumulator already holds x log2(e)
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(__uint_as_float(vv[cur][q]), 120.0f)));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(__uint_as_float(vv[cur][q + 1]), 120.0f)));
         f2_unpack(f2_add(f2_pack(e0, e1), kOne), l0, l1);
         asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(l0));
         asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l1) : "f"(l1));
