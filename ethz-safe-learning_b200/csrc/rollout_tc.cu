@@ -30,9 +30,11 @@
 //     Gaussian draws (tc_head.cuh), parked as bf16 pairs in shared memory (two-tile variant) or
 //     registers (one-tile variant);
 //   * the rollout state s_t (fp32) lives in spare TMEM columns next to the accumulators. The
-//     Gaussian-head / state / scoring pass is tc_head.cuh's head_step_pass (shared with
-//     rollout_tc_wide.cu). The per-row min over slices owned by different threads goes through a small
-//     shared-memory exchange and one named barrier per step and tile, off the MMA critical path.
+//     Gaussian-head / state pass is tc_head.cuh's head_step_pass (shared with rollout_tc_wide.cu); it
+//     publishes each thread's partial lidar minima in a small shared-memory exchange;
+//   * ONE SCORER WARP PER TILE combines those partials into goal distance / cost per row and keeps
+//     the per-row objective (reward, done masks, cost bits), so that no epilogue warp and no tile-wide
+//     barrier sits between a head pass and the next step's layer 0.
 #include <cuda_bf16.h>
 
 #include <cstdlib>
@@ -125,6 +127,8 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
   const int O = g.O, A = g.A;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool l0_pad_bias = (O + A + 2 <= 64);     // layer-0 bias rides in the K padding (see pack in api.cu)
+  constexpr int n_quarters = 4;                   // TMEM lane quarters (= warps per column group) of a tile
+  constexpr int tile_bar_threads = Q * 128 + 32;  // a tile's epilogue warps + one partner warp (issuer / scorer)
 
   // ---- shared memory carve-up (base is 1024-aligned: required by SWIZZLE_128B) -------------------
   const uint32_t w_bytes = kAtomBytes + (uint32_t)L * 2 * kAtomBytes;     // layer 0: 1 atom; others: 2
@@ -208,16 +212,16 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
         uint32_t* my_rs = rs_smem + j * 8 * 128 + lane;                    // [8 fields][128 rows]
         const float* part_tile = part_smem + (j * Q * nparts) * 128;       // [Q][nparts][128 rows]
 #pragma unroll 1
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < n_quarters; ++i) {
           const int row = lane + 32 * i;
 #pragma unroll
           for (int f = 0; f < 7; ++f) my_rs[f * 128 + 32 * i] = 0u;
           my_rs[7 * 128 + 32 * i] = row < tis.count ? (uint32_t)decode_row(g, tis.member, tis.k0 + row).out : 0xffffffffu;
         }
         for (int ts = -1; ts < H; ++ts) {                                  // ts = -1: distance / cost of s_0
-          named_bar_sync<kTileThreads + 32>(kBarPart + j);
+          named_bar_sync_n(kBarPart + j, tile_bar_threads);
 #pragma unroll 1
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < n_quarters; ++i) {
             uint32_t* q = my_rs + 32 * i;
             float nd, nc;
             head_combine<Q>(sc, part_tile + lane + 32 * i, nparts, nd, nc);
@@ -242,11 +246,11 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
               q[6 * 128] = rs.done ? 1u : 0u;
             }
           }
-          if (ts + 1 < H) named_bar_arrive<kTileThreads + 32>(kBarFree + j);
+          if (ts + 1 < H) named_bar_arrive_n(kBarFree + j, tile_bar_threads);
         }
         if (prm.row_return != nullptr) {
 #pragma unroll 1
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < n_quarters; ++i) {
             const uint32_t* q = my_rs + 32 * i;
             const uint32_t slot = q[7 * 128];
             if (slot != 0xffffffffu) {
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
           const int tl_t = t;
 #endif
           for (int layer = 0; layer <= L; ++layer) {
-            named_bar_sync<kTileThreads + 32>(kBarA + j);     // every epilogue warp's slice of this layer's A is in TMEM
+            named_bar_sync_n(kBarA + j, tile_bar_threads);     // every epilogue warp's slice of this layer's A is in TMEM
             tc_fence_after();
             TL(2 * layer);
             if (elect_one()) {                                // ptxas must KNOW one lane is active: with a plain
@@ -317,7 +321,7 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
             mbar_wait(bar_acc, ph);                           // the layer's MMAs have completed
             ph ^= 1;
             tc_fence_before();
-            named_bar_arrive<kTileThreads + 32>(kBarAcc + j); // wake the tile's epilogue warps
+            named_bar_arrive_n(kBarAcc + j, tile_bar_threads); // wake the tile's epilogue warps
           }
         }
       }
@@ -372,10 +376,10 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
         auto publish_a = [&]() {
           tmem_st_wait();
           tc_fence_before();
-          named_bar_arrive<kTileThreads + 32>(kBarA + j);
+          named_bar_arrive_n(kBarA + j, tile_bar_threads);
         };
         auto wait_accumulator = [&]() {
-          named_bar_sync<kTileThreads + 32>(kBarAcc + j);     // released by the issuer warp's arrive
+          named_bar_sync_n(kBarAcc + j, tile_bar_threads);     // released by the issuer warp's arrive
           tc_fence_after();
         };
 
@@ -417,7 +421,20 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
           if (eps_row != nullptr) {
             z = external_noise8_bf16(eps_row + t * eps_step, o0, O);
           } else {
+#ifdef SIMBA_TC_TIMELINE
+            {
+              PhiloxState p{(uint32_t)(o0 >> 3), row32, (uint32_t)t | c2_base, c3_noise, key.x, key.y};
+              TL(50);
+              philox_rounds<10>(p);
+              if (p.c0 == 0x12345u) TL(53);
+              TL(51);
+              z = philox_finish_noise8_bf16(p);
+              if (z.x == 0x12345u) TL(53);
+              TL(52);
+            }
+#else
             z = philox_noise8_bf16(key, (uint32_t)(o0 >> 3), row32, (uint32_t)t | c2_base, c3_noise);
+#endif
             if (o0 + 8 > O) {                               // padded outputs draw nothing (their delta is 0)
               uint32_t w[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
@@ -434,7 +451,7 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
         head_first_pass<OW>(hc, astore, s0_ptr, row_ok, act_pf);
         prefetch_actions(1);
         publish_a();                                        // layer-0 input of step 0
-        named_bar_arrive<kTileThreads + 32>(kBarPart + j);  // partial minima of s_0 published (scorer warp)
+        named_bar_arrive_n(kBarPart + j, tile_bar_threads);  // partial minima of s_0 published (scorer warp)
 
         for (int t = 0; t < H; ++t) {
 #ifdef SIMBA_TC_TIMELINE
@@ -476,13 +493,13 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
 
           // ---- Gaussian heads + state update + next input + partial minima (one fused pass) --------
           wait_accumulator();
-          named_bar_sync<kTileThreads + 32>(kBarFree + j);  // the scorer warp is done with the previous partials
+          named_bar_sync_n(kBarFree + j, tile_bar_threads);  // the scorer warp is done with the previous partials
           TL(40);
           if (prm.sampling_propagation) head_step_pass<OW, true>(hc, noise, astore, t + 1 < H);
           else head_step_pass<OW, false>(hc, noise, astore, t + 1 < H);
           TL(41);
           if (t + 1 < H) publish_a();                       // next step's layer 0 goes out
-          named_bar_arrive<kTileThreads + 32>(kBarPart + j);  // partial minima of s_{t+1} published (scorer warp)
+          named_bar_arrive_n(kBarPart + j, tile_bar_threads);  // partial minima of s_{t+1} published (scorer warp)
           TL(42);
         }
       }

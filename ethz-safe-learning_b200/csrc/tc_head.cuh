@@ -37,19 +37,30 @@ __device__ __forceinline__ uint32_t box_muller_pair_bf16(uint32_t w) {
   return pack_bf16(r * cs, r * sn);
 }
 
+struct PhiloxState {
+  uint32_t c0, c1, c2, c3, k0, k1;
+};
+template <int kRounds>
+__device__ __forceinline__ void philox_rounds(PhiloxState& p) {
+#pragma unroll
+  for (int r = 0; r < kRounds; ++r) {
+    uint32_t lo0, hi0, lo1, hi1;                          // one IMAD.WIDE per product
+    asm("{\n\t.reg .b64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo0), "=r"(hi0) : "r"(p.c0), "r"(kPhiloxM0));
+    asm("{\n\t.reg .b64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo1), "=r"(hi1) : "r"(p.c2), "r"(kPhiloxM1));
+    const uint32_t n0 = hi1 ^ p.c1 ^ p.k0, n2 = hi0 ^ p.c3 ^ p.k1;
+    p.c1 = lo1; p.c3 = lo0; p.c0 = n0; p.c2 = n2;
+    p.k0 += kPhiloxW0; p.k1 += kPhiloxW1;
+  }
+}
+__device__ __forceinline__ uint4 philox_finish_noise8_bf16(const PhiloxState& p) {
+  return make_uint4(box_muller_pair_bf16(p.c0), box_muller_pair_bf16(p.c1), box_muller_pair_bf16(p.c2),
+                    box_muller_pair_bf16(p.c3));
+}
 __device__ __forceinline__ uint4 philox_noise8_bf16(uint2 key, uint32_t c0, uint32_t c1, uint32_t c2,
                                                     uint32_t c3) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t lo0, hi0, lo1, hi1;                          // one IMAD.WIDE per product
-    asm("{\n\t.reg .b64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo0), "=r"(hi0) : "r"(c0), "r"(kPhiloxM0));
-    asm("{\n\t.reg .b64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo1), "=r"(hi1) : "r"(c2), "r"(kPhiloxM1));
-    const uint32_t n0 = hi1 ^ c1 ^ key.x, n2 = hi0 ^ c3 ^ key.y;
-    c1 = lo1; c3 = lo0; c0 = n0; c2 = n2;
-    key.x += kPhiloxW0; key.y += kPhiloxW1;
-  }
-  return make_uint4(box_muller_pair_bf16(c0), box_muller_pair_bf16(c1), box_muller_pair_bf16(c2),
-                    box_muller_pair_bf16(c3));
+  PhiloxState p{c0, c1, c2, c3, key.x, key.y};
+  philox_rounds<10>(p);
+  return philox_finish_noise8_bf16(p);
 }
 
 // externally supplied draws (parity mode): 8 consecutive floats of one row, zero beyond O

@@ -221,6 +221,14 @@ __device__ __forceinline__ void named_bar_arrive(int id) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kThreads) : "memory");
 }
 
+// the same with the thread count in a register
+__device__ __forceinline__ void named_bar_sync_n(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive_n(int id, int threads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (dense 128 B rows)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;

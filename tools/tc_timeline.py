@@ -45,8 +45,8 @@ if wl == 'c5':                     # rollout_tc_wide.cu keeps the round-1 event 
             print(' '.join(line))
     sys.exit(0)
 # rollout_tc.cu: epilogue warps stamp 0 (step start), per hidden layer l: 1+4l accumulator ready, 2+4l drained,
-# 3+4l A slice published, 4+4l noise block done; 40 head accumulator ready, 41 head pass done, 42 published,
-# 43 scored. The issuer warp of tile 0 (who = 2) stamps 2*layer (A ready seen) and 2*layer+1 (layer committed).
+# 3+4l A slice published (+ deferred scoring at l = 0), 4+4l noise block done; 40 head accumulator ready,
+# 41 head pass done, 42 published. The issuer warp of tile 0 (who = 2) stamps 2*layer (A ready seen) and 2*layer+1 (layer committed).
 for who, name in ((0, 'epilogue warp 0 of tile 0'), (1, 'last epilogue warp of tile 0')):
     print("==", name, "(cycles since the step's start)")
     for step in range(2, min(H - 1, 8)):
@@ -56,9 +56,13 @@ for who, name in ((0, 'epilogue warp 0 of tile 0'), (1, 'last epilogue warp of t
         for l in range(L):
             line.append("L%d acc->%5d drained->%5d published->%5d noise->%5d |" % (
                 l, ev[1 + 4 * l] - base, ev[2 + 4 * l] - base, ev[3 + 4 * l] - base, ev[4 + 4 * l] - base))
-        line.append("head acc->%5d pass->%5d published->%5d scored->%5d  total %5d" % (
-            ev[40] - base, ev[41] - base, ev[42] - base, ev[43] - base, t[who, step + 1][0] - base))
+        line.append("head acc->%5d pass->%5d published->%5d  total %5d" % (
+            ev[40] - base, ev[41] - base, ev[42] - base, t[who, step + 1][0] - base))
         print(' '.join(line))
+print("== noise block detail, epilogue warp 0 (last block of the step): philox rounds / box-muller cycles")
+for step in range(2, min(H - 1, 8)):
+    ev = t[0, step]
+    print("step %2d philox %5d  box-muller %5d" % (step, ev[51] - ev[50], ev[52] - ev[51]))
 print("== issuer warp of tile 0 (cycles since epilogue warp 0's step start; layer: A-ready seen -> committed)")
 for step in range(2, min(H - 1, 8)):
     base = t[0, step][0]
