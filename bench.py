@@ -112,25 +112,53 @@ class ClockSampler(object):
 # ------------------------------------------------------------------------------------------------
 # CPU planner (the oracle port) — cpu_baseline leg and --impl reference
 # ------------------------------------------------------------------------------------------------
-def time_cpu_planner(c, budget_s=20.0, max_plans=12):
-    """Times the numpy restatement of the reference planner (oracle/simba_oracle.py) on this box's
-    host cores: whole C1 plans with Philox-contract normals pre-generated outside the timed region."""
+def _cpu_planners(c, objective='penalty'):
+    """The two CPU restatements of the reference planner (oracle/simba_oracle.py: numpy;
+    oracle/torch_ref.py: torch-CPU, shaped like the reference) as plan(state, z, eps, zf) callables."""
     from oracle import simba_oracle as so           # the only product-side use: the CPU baseline
+    from oracle import torch_ref
     from tests import helpers
+    pn = helpers.oracle_planner(c, objective)
+    cfg = dict(so.DEFAULT_SCORER_CONFIG)
+    dyn = torch_ref.Dynamics(torch_ref.Ensemble(c['weights']), c['smin'], c['smax'], True, True)
+    pt = torch_ref.Planner(dyn, torch_ref.GoalScorer(cfg, c['table']), [-1.0] * c['A'], [1.0] * c['A'], c['H'],
+                           c['I'], 0.0, c['N'], c['K'], c['P'], 0.0, 0.01, posterior_mean_threashold=0.15,
+                           objective=objective)
+    return {"numpy": lambda st, z, eps, zf: pn.do_generate_action(st, z, eps, zf)[2],
+            "torch": lambda st, z, eps, zf: pt.do_generate_action(st, z, eps, zf)[2]}
+
+
+def time_cpu_planner(c, budget_s=20.0, max_plans=12, label="C1"):
+    """Times the CPU restatements of the reference planner on this box's host cores: whole plans with
+    the normal draws pre-generated outside the timed region. Both restatements (numpy and torch-CPU,
+    cross-checked against each other and against fixtures produced by the unmodified reference code) get
+    two plans each; the faster one is the baseline and gets the rest of the budget."""
     from simba_b200 import synthetic
     z, eps, zf = synthetic.make_draws(c['I'], 1, c['N'], c['H'], c['A'], c['P'], c['O'], seed=2)
-    pl = helpers.oracle_planner(c, 'penalty')
+    z, eps, zf = z[:, 0], eps[:, 0], zf[0]
     try:
         # torchrun exports OMP_NUM_THREADS=1; the CPU planner is allowed every host thread it can use
         import threadpoolctl
         threadpoolctl.threadpool_limits(limits=os.cpu_count())
+        import torch
+        torch.set_num_threads(os.cpu_count())
     except Exception:
         pass
-    pl.do_generate_action(c['state'], z[:, 0], eps[:, 0], zf[0])          # warm-up (BLAS threads, pages)
-    times, t_start = [], time.perf_counter()
-    while len(times) < max_plans and (time.perf_counter() - t_start < budget_s or len(times) < 2):
+    planners = _cpu_planners(c)
+    probe, n = {}, c['I']
+    t_start = time.perf_counter()
+    for name, fn in planners.items():
+        fn(c['state'], z, eps, zf)                                          # warm-up (BLAS threads, pages)
         t0 = time.perf_counter()
-        _, _, n = pl.do_generate_action(c['state'], z[:, 0], eps[:, 0], zf[0])
+        n = fn(c['state'], z, eps, zf)
+        probe[name] = time.perf_counter() - t0
+        if time.perf_counter() - t_start > budget_s and len(probe) == 1:  # very large workloads: one is enough
+            break
+    best_name = min(probe, key=probe.get)
+    fn, times = planners[best_name], [probe[best_name]]
+    while len(times) < max_plans and time.perf_counter() - t_start < budget_s:
+        t0 = time.perf_counter()
+        n = fn(c['state'], z, eps, zf)
         times.append(time.perf_counter() - t0)
     best, med = min(times), float(np.median(times))
     try:
@@ -139,9 +167,11 @@ def time_cpu_planner(c, budget_s=20.0, max_plans=12):
     except Exception:
         threads = os.cpu_count()
     return {"value": 1.0 / med, "unit": UNIT, "cores": int(threads), "kind": "port",
-            "sample": "%d whole C1 plans (numpy fp32 restatement of the TensorFlow reference, "
-                      "BLAS threads=%d of %d host cpus); median %.1f ms, best %.1f ms per plan"
-                      % (len(times), threads, os.cpu_count(), med * 1e3, best * 1e3),
+            "sample": "%d whole %s plans on the %s fp32 restatement of the TensorFlow reference (the faster of "
+                      "the two restatements here: %s), threads=%d of %d host cpus; median %.1f ms, best %.1f ms per plan"
+                      % (len(times), label, best_name,
+                         ", ".join("%s %.0f ms" % kv for kv in sorted(probe.items())), threads, os.cpu_count(),
+                         med * 1e3, best * 1e3),
             "transitions_per_s": n * c['H'] * c['P'] * c['N'] / med, "ms_per_plan_median": med * 1e3}
 
 
@@ -173,7 +203,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
-    ap.add_argument('--extras', default=None, help="comma list of: c3, c4, c5, fp32, train (default: c3 when N > 1, c4,c3,c5,train when N == 1)")
+    ap.add_argument('--extras', default=None, help="comma list of: c3, c4, c5, fp32, train, none (default: c3,c4 when N > 1, fp32,c4,c3,c5,train when N == 1)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -198,14 +228,7 @@ def main():
     c = synthetic.make_workload('c1')
     precision = args.precision
     pol = synthetic.build_policy(c, 'penalty', precision=precision, seed=0x5EED + 1000 * rank)
-    try:
-        pol.build()
-    except _lib.SimbaError as e:
-        if e.code != -6:
-            raise
-        precision = 'fp32'
-        pol = synthetic.build_policy(c, 'penalty', precision=precision, seed=0x5EED + 1000 * rank)
-        pol.build()
+    pol.build()                 # fails loudly if the requested precision is not offered for this shape
     n_pool = 16
     states_np = synthetic.make_state(c['sensors'], seed=100 + rank, n_states=n_pool)
     states = torch.from_numpy(states_np).cuda()
@@ -300,12 +323,13 @@ def main():
     peak_tf = peaks.get('bf16_tflops', 1590.0)
     achieved_tf = flops_per_launch / (roll_ms * 1e-3) / 1e12
     ms_plan = ms.mean()
-    roofline = {"kernel": "rollout_tc_kernel" if precision == 'bf16' else "rollout_f32_kernel",
+    kernel_name = "rollout_tc_kernel<1,4>" if precision == 'bf16' else "rollout_f32_kernel"
+    roofline = {"kernel": kernel_name,
                 "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                # dram__bytes_read.sum + dram__bytes_write.sum of one rollout_tc_kernel launch at this shape from
-                # the committed ncu --set full capture (profiles/r01_v4_c1_rollout_tc.txt): weights + actions
-                # are read once, outputs stay in L2 -> nowhere near HBM-bound
-                "frac": achieved_tf / peak_tf, "traffic": 841728 if precision == 'bf16' else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the CURRENT kernel at this shape,
+                # from the committed ncu --set full capture (profiles/kernel_traffic.json, written by
+                # tools/ncu_traffic.py); null when no capture of this kernel version is committed
+                "frac": achieved_tf / peak_tf, "traffic": committed_traffic(kernel_name + "@c1"),
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PFLOP/s",
                 "flops_per_launch": flops_per_launch, "launch_ms": roll_ms,
                 "share_of_plan": c['I'] * roll_ms / ms_plan,
@@ -327,17 +351,17 @@ def main():
     # ---- extras -----------------------------------------------------------------------------------
     extras = {}
     if args.extras is None:
-        args.extras = 'c3' if world > 1 else 'c4,c3,c5,train'
+        args.extras = 'c3,c4' if world > 1 else 'fp32,c4,c3,c5,train'
     want = [x for x in args.extras.split(',') if x]
     try:
         if 'fp32' in want and precision != 'fp32':
             extras['fp32'] = bench_plain(synthetic, torch, c, 'fp32', states, flush, min(K, 50))
         if 'c4' in want:
-            extras['c4'] = bench_batched(synthetic, torch, precision, flush, world, rank)
+            extras['c4'] = bench_batched(synthetic, torch, dist, precision, flush, world, rank)
         if 'c3' in want:
-            extras['c3'] = bench_c3(synthetic, torch, dist, lib, _lib, precision, world, rank)
+            extras['c3'] = bench_c3(synthetic, torch, dist, lib, _lib, precision, world, rank, flush)
         if 'c5' in want and rank == 0:
-            extras['c5'] = bench_wide(synthetic, torch, flush)
+            extras['c5'] = bench_wide(synthetic, torch, flush, cpu=not args.no_cpu_baseline and world == 1)
         if 'train' in want and rank == 0:
             extras['train'] = bench_train(torch, cpu=not args.no_cpu_baseline and world == 1)
     except Exception as e:                      # extras never take the headline line down
@@ -355,6 +379,7 @@ def main():
         # whole planning calls, so it includes the small CEM kernels (< 1 % of the time there)
         tf = extras['c4']['tflops_per_gpu']
         line['roofline_large'] = {"kernel": "rollout_tc_kernel<2,2>" if precision == 'bf16' else "rollout_f32_kernel",
+                                  "traffic_rollout_launch": committed_traffic("rollout_tc_kernel<2,2>@c4_256states"),
                                   "workload": "configs[3]: %d states x C1 per GPU" % extras['c4']['states_per_call_per_gpu'],
                                   "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
                                   "frac": tf / peak_tf, "traffic": None,
@@ -366,6 +391,15 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def committed_traffic(key):
+    """DRAM bytes per launch of a kernel from the committed ncu capture of the current kernel version."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, 'profiles', 'kernel_traffic.json')))[key]
+        return rec['dram_bytes_per_launch']
+    except Exception:
+        return None
 
 
 def bench_plain(synthetic, torch, c, precision, states, flush, K):
@@ -384,15 +418,17 @@ def bench_plain(synthetic, torch, c, precision, states, flush, K):
     return {"plans_per_s": 1e3 / ms, "ms_per_plan": ms, "precision": precision}
 
 
-def bench_wide(synthetic, torch, flush):
-    """BASELINE configs[4]: the wide 10 x (4 x 400) ensemble, horizon 50 — single-state plans on the
-    streaming tcgen05 kernel (bf16) and on the fp32 kernel, plus 5 and 20 states per call (120 / 480
-    row tiles) for the kernel's throughput."""
+def bench_wide(synthetic, torch, flush, cpu=True):
+    """BASELINE configs[4]: the wide 10 x (4 x 400) ensemble, horizon 50 — safety-aware (SafeCemMpc,
+    penalty) and safety-unaware (CemMpc, reward-only elites) single-state plans on the streaming tcgen05
+    kernel (bf16), the fp32 kernel beside it, plus 5 and 20 states per call (120 / 480 row tiles) for the
+    kernel's throughput, and one plan of the CPU restatement on the host cores."""
     out = {}
     fpt = None
-    for precision, S in (('bf16', 1), ('fp32', 1), ('bf16', 5), ('bf16', 20)):
+    for objective, precision, S in (('penalty', 'bf16', 1), ('reward', 'bf16', 1), ('penalty', 'fp32', 1),
+                                    ('penalty', 'bf16', 5), ('penalty', 'bf16', 20), ('reward', 'bf16', 20)):
         c = synthetic.make_workload('c5', S=S, seed=0)
-        pol = synthetic.build_policy(c, 'penalty', precision=precision, seed=31)
+        pol = synthetic.build_policy(c, objective, precision=precision, seed=31)
         st = torch.from_numpy(synthetic.make_state(c['sensors'], seed=500, n_states=S).reshape(S, -1)).cuda()
         pol.plan_device(st)
         torch.cuda.synchronize()
@@ -407,9 +443,14 @@ def bench_wide(synthetic, torch, flush):
         ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
         fpt = synthetic.flops_per_transition(c['O'], c['A'], c['L'], c['U'])
         trans = c['I'] * c['H'] * c['P'] * c['N'] * S
-        out["%s_%dstate" % (precision, S)] = {"ms_per_call": ms, "plans_per_s": S * 1e3 / ms,
-                                              "tflops": trans * fpt / (ms * 1e-3) / 1e12}
+        tag = "%s_%dstate" % (precision, S) if objective == 'penalty' else "%s_%dstate_reward_only" % (precision, S)
+        out[tag] = {"objective": "SafeCemMpc penalty" if objective == 'penalty' else "CemMpc reward-only",
+                    "ms_per_call": ms, "plans_per_s": S * 1e3 / ms, "tflops": trans * fpt / (ms * 1e-3) / 1e12}
     out["workload"] = "configs[4]: E=10 L=4x400 O=60 A=2 H=50 N=150 P=20 I=5; %d flop per transition" % fpt
+    if cpu:
+        c = synthetic.make_workload('c5', S=1, seed=0)
+        cb = time_cpu_planner(c, budget_s=30.0, max_plans=2, label="configs[4] (C5)")
+        out["cpu_baseline"] = cb
     return out
 
 
@@ -467,15 +508,22 @@ def bench_train(torch, cpu=True, steps=1000, rows=24000):
     return out
 
 
-def bench_batched(synthetic, torch, precision, flush, world, rank, S=1024):
-    """BASELINE configs[3]: S independent states per call (sharded over ranks, no collective)."""
+def bench_batched(synthetic, torch, dist, precision, flush, world, rank, S=1024):
+    """BASELINE configs[3]: S independent states per call, sharded over the ranks (no data-path
+    collective). Device-timed per rank (max over ranks), and once end to end through
+    simba_b200.distributed.plan_states_sharded (host states in, all S actions out on every rank)."""
+    from simba_b200 import distributed as sd
     S_local = S // world
     c = synthetic.make_workload('c1', S=S_local, seed=0)
-    pol = synthetic.build_policy(c, 'penalty', precision=precision, seed=11 + rank)
-    st = torch.from_numpy(synthetic.make_state(c['sensors'], seed=300 + rank, n_states=S_local)).cuda()
+    pol = synthetic.build_policy(c, 'penalty', precision=precision, seed=11)
+    states_all = synthetic.make_state(c['sensors'], seed=300, n_states=S)          # same on every rank
+    lo, hi = sd.shard_bounds(S, world, rank)
+    st = torch.from_numpy(np.ascontiguousarray(states_all[lo:hi])).cuda()
     for _ in range(2):
         pol.plan_device(st)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     K = 5
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     for k in range(K):
@@ -484,17 +532,35 @@ def bench_batched(synthetic, torch, precision, flush, world, rank, S=1024):
         pol.plan_device(st)
         ev[k][1].record()
     torch.cuda.synchronize()
-    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    t = torch.tensor([np.mean([a.elapsed_time(b) for a, b in ev])], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.cpu()[0])
     fpt = synthetic.flops_per_transition(c['O'], c['A'], c['L'], c['U'])
     trans = c['I'] * c['H'] * c['P'] * c['N'] * S_local
-    return {"states_per_call_per_gpu": S_local, "ms_per_call": ms, "plans_per_s_per_gpu": S_local * 1e3 / ms,
-            "transitions_per_s_per_gpu": trans / (ms * 1e-3), "tflops_per_gpu": trans * fpt / (ms * 1e-3) / 1e12}
+    out = {"states_per_call_per_gpu": S_local, "states_per_call_total": S, "ms_per_call": ms,
+           "plans_per_s_per_gpu": S_local * 1e3 / ms, "plans_per_s_total": S * 1e3 / ms,
+           "transitions_per_s_per_gpu": trans / (ms * 1e-3), "tflops_per_gpu": trans * fpt / (ms * 1e-3) / 1e12,
+           "scaling": "strong (1024 states split over the ranks)"}
+    if world > 1:
+        # the public sharded call: every rank passes all S states, gets all S actions
+        dist.barrier()
+        t0 = time.perf_counter()
+        acts = sd.plan_states_sharded(pol, states_all)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out["plan_states_sharded"] = {"ms_per_call_e2e": dt * 1e3, "actions_shape": list(acts.shape),
+                                      "all_finite": bool(np.all(np.isfinite(acts)))}
+    return out
 
 
-def bench_c3(synthetic, torch, dist, lib, _lib, precision, world, rank):
+def bench_c3(synthetic, torch, dist, lib, _lib, precision, world, rank, flush):
     """BASELINE configs[2]: population 65536, 32 particles, horizon 30, sharded over the ranks with one
     NCCL all-gather of (return, cost) per iteration. E=5 does not divide P=32 (the reference's tf.split
-    would raise) -> member_map='particle'."""
+    would raise) -> member_map='particle'. Five timed plans, L2 flushed between them; a per-iteration
+    breakdown from CUDA events around single launches of each stage; at N > 1 rank 0 also runs the same
+    plan unsharded and reports whether the sharded plan reproduces it bit for bit."""
+    import ctypes as C
     c = synthetic.make_workload('c3')
     pol, ok = None, 1.0
     try:
@@ -518,13 +584,15 @@ def bench_c3(synthetic, torch, dist, lib, _lib, precision, world, rank):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    K = 2
+    K = 5
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     outs = []
     for k in range(K):
+        flush.fill_(k & 0xff)
         ev[k][0].record()
-        outs.append(pol.plan_device(st, seed=5 + k)[0].clone())
+        a_k, s_k = pol.plan_device(st, seed=5 + k)[:2]
         ev[k][1].record()
+        outs.append(torch.cat([a_k.reshape(-1).clone(), s_k.reshape(-1).clone()]))
     torch.cuda.synchronize()
     t = torch.tensor([np.mean([a.elapsed_time(b) for a, b in ev])], dtype=torch.float64, device='cuda')
     same = torch.ones(1, device='cuda')
@@ -537,9 +605,63 @@ def bench_c3(synthetic, torch, dist, lib, _lib, precision, world, rank):
     ms = float(t.cpu()[0])
     fpt = synthetic.flops_per_transition(c['O'], c['A'], c['L'], c['U'])
     trans = c['I'] * c['H'] * c['P'] * c['N']
-    return {"ms_per_plan": ms, "plans_per_s": 1e3 / ms, "transitions_per_s": trans / (ms * 1e-3),
-            "tflops_total": trans * fpt / (ms * 1e-3) / 1e12, "replicas_bit_identical": bool(same.cpu()[0] > 0),
-            "member_map": "particle", "scaling": "strong"}
+    out = {"ms_per_plan": ms, "plans_per_s": 1e3 / ms, "transitions_per_s": trans / (ms * 1e-3),
+           "tflops_total": trans * fpt / (ms * 1e-3) / 1e12, "replicas_bit_identical": bool(same.cpu()[0] > 0),
+           "member_map": "particle", "scaling": "strong", "timed_plans": K, "l2": "flushed between timed plans"}
+
+    # ---- per-iteration breakdown: each stage launched alone, CUDA events, this rank's shard --------
+    pl = pol._ensure_planner()
+    S, N, H, A, P_, O, Kel = 1, c['N'], c['H'], c['A'], c['P'], c['O'], c['K']
+    Nl = N // world
+    f32 = dict(dtype=torch.float32, device='cuda')
+    mu = torch.zeros((S, H, A), **f32); sg = torch.ones((S, H, A), **f32)
+    acts = torch.empty((S, N, H, A), **f32)
+    ret = torch.empty((S, P_, Nl), **f32); msk = torch.empty((S, P_, Nl), dtype=torch.int64, device='cuda')
+    csum = torch.empty((S, P_, Nl), **f32)
+    pl_local = torch.empty((S, Nl, 2), **f32); pairs = torch.empty((world, S, Nl, 2), **f32)
+    elite = torch.empty((S, Kel), dtype=torch.int32, device='cuda')
+    best_a = torch.zeros((S, A), **f32); best_s = torch.full((S,), -np.inf, **f32)
+    active = torch.ones((S,), dtype=torch.int32, device='cuda'); iters = torch.zeros((S,), dtype=torch.int32, device='cuda')
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t_: C.c_void_p(t_.data_ptr())
+    stages = [
+        ('sample', lambda i: lib.simba_sample_actions(pl, p(mu), p(sg), None, 3, i, None, p(acts), sp)),
+        ('rollout', lambda i: lib.simba_rollout_score(pl, p(st), p(acts), None, 3, i, None, p(ret), p(msk), p(csum), sp)),
+        ('reduce', lambda i: lib.simba_score_reduce(pl, p(ret), p(msk), p(csum), None, p(pl_local), sp)),
+        ('all_gather', lambda i: lib.simba_allgather_scores(pl, p(pl_local), p(pairs), sp)),
+        ('select', lambda i: lib.simba_select_elites(pl, p(pairs), p(acts), None, p(elite), None, p(best_a), p(best_s), sp)),
+        ('refit', lambda i: lib.simba_refit(pl, p(acts), p(elite), p(mu), p(sg), p(active), p(iters), sp)),
+    ]
+    breakdown = {}
+    for name, fn in stages:
+        _lib.check(fn(0))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ts = []
+        for i in range(3):
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(); _lib.check(fn(i + 1)); b_.record(); torch.cuda.synchronize()
+            ts.append(a_.elapsed_time(b_))
+        breakdown[name + "_us"] = 1e3 * float(np.mean(ts))
+    rest = sum(v for k_, v in breakdown.items() if k_ != 'rollout_us')
+    breakdown["not_rollout_share"] = rest / max(1e-9, rest + breakdown['rollout_us'])
+    breakdown["note"] = ("single launches incl. ~5-8 us launch latency each; inside the plan's CUDA graph the small "
+                         "stages are shorter")
+    out["per_iteration_breakdown"] = breakdown
+
+    # ---- sharded == unsharded (rank 0 runs the whole population alone) ----------------------------
+    if world > 1:
+        eq = torch.ones(1, device='cuda')
+        if rank == 0:
+            solo = synthetic.build_policy(c, 'penalty', precision=precision, member_map='particle', seed=21)
+            a1, s1 = solo.plan_device(st, seed=5 + K - 1)[:2]
+            torch.cuda.synchronize()
+            single = torch.cat([a1.reshape(-1), s1.reshape(-1)])
+            eq = (single == outs[-1]).all().float().reshape(1)
+        dist.broadcast(eq, 0)
+        out["sharded_equals_single"] = bool(eq.cpu()[0] > 0)
+    return out
 
 
 if __name__ == '__main__':

@@ -939,7 +939,7 @@ static RefitParams make_refit_params(simba_planner_t* p, const float* actions, c
   rp.smoothing = p->cfg.smoothing;
   rp.one_minus_smoothing = (float)(1.0 - (double)p->cfg.smoothing);
   rp.stddev_threshold = p->cfg.stddev_threshold;
-  rp.actions = actions; rp.elite = elite; rp.mu = mu; rp.sigma = sigma; rp.active = active;
+  rp.actions = const_cast<float*>(actions); rp.elite = elite; rp.mu = mu; rp.sigma = sigma; rp.active = active;
   rp.iterations_run = iterations_run;
   return rp;
 }
@@ -1065,10 +1065,13 @@ static int enqueue_plan(simba_planner* p, cudaStream_t st, int* n_launches) {
   for (int it = 0; it < c.iterations; ++it) {
     const float* z = p->ext_z_actions ? p->ext_z_actions + (size_t)it * S * N * HA : nullptr;
     const float* eps = p->ext_eps ? p->ext_eps + (size_t)it * S * c.horizon * B * O : nullptr;
-    int rc = do_sample_actions(p, p->mu, p->sigma, z, 0, sp, it, p->active, p->actions, st);
-    if (rc) return rc; ++launches;
-    rc = do_rollout_score(p, p->d_states, p->actions, eps, 0, sp, it, p->active, p->row_ret,
-                          p->row_cmask, p->row_csum, st);
+    // population sharding: this rank samples only the candidates it rolls out; selection and refit
+    // recompute the elite rows the other ranks sampled (SURVEY.md section 8 e)
+    SampleParams smp = make_sample_params(p, p->mu, p->sigma, z, 0, sp, it, p->active, p->actions);
+    if (multi) { smp.cand0 = p->geom.cand0; smp.n_cand = p->geom.N_local; }
+    CUDA_TRY(launch_sample_actions(smp, st)); ++launches;
+    int rc = do_rollout_score(p, p->d_states, p->actions, eps, 0, sp, it, p->active, p->row_ret,
+                              p->row_cmask, p->row_csum, st);
     if (rc) return rc; ++launches;
     rc = simba_score_reduce(p, p->row_ret, p->row_cmask, p->row_csum, p->active, p->pairs_local, st);
     if (rc) return rc; ++launches;
@@ -1076,11 +1079,12 @@ static int enqueue_plan(simba_planner* p, cudaStream_t st, int* n_launches) {
       rc = simba_allgather_scores(p, p->pairs_local, p->pairs_all, st);
       if (rc) return rc; ++launches;
     }
-    rc = simba_select_elites(p, pairs_all, p->actions, p->active, p->elite, nullptr, p->best_action,
-                             p->best_score, st);
-    if (rc) return rc; ++launches;
-    rc = simba_refit(p, p->actions, p->elite, p->mu, p->sigma, p->active, p->iters, st);
-    if (rc) return rc; ++launches;
+    SelectParams slp = make_select_params(p, pairs_all, p->actions, p->active, p->elite, nullptr,
+                                          p->best_action, p->best_score);
+    RefitParams rfp = make_refit_params(p, p->actions, p->elite, p->mu, p->sigma, p->active, p->iters);
+    if (multi) { slp.regen = 1; slp.sample = smp; rfp.regen = 1; rfp.sample = smp; }
+    CUDA_TRY(launch_select_elites(slp, st)); ++launches;
+    CUDA_TRY(launch_refit(rfp, st)); ++launches;
   }
   int rc = do_finalize_action(p, p->best_action, p->ext_z_final, 0, sp, p->d_out_action, st);
   if (rc) return rc; ++launches;

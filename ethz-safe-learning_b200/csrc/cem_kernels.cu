@@ -16,7 +16,7 @@ namespace simba {
 // One thread = 4 consecutive flattened (h, a) elements of one candidate (= one Philox block).
 // =============================================================================================
 // one Philox block = 4 consecutive flattened (h, a) elements of candidate i of state s
-__device__ __forceinline__ void sample_block(const SampleParams& p, int s, int i, int j) {
+__device__ __forceinline__ void sample_values4(const SampleParams& p, int s, int i, int j, float (&out)[4]) {
   const int HA = p.H * p.A;
   const long base = ((long)s * p.N + i) * HA + 4 * j;
   float z[4];
@@ -28,7 +28,6 @@ __device__ __forceinline__ void sample_block(const SampleParams& p, int s, int i
                                            (uint32_t)s, (uint32_t)p.iteration, 0u, (uint32_t)i, (uint32_t)j);
     z[0] = n.x; z[1] = n.y; z[2] = n.z; z[3] = n.w;
   }
-  float out[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int e = 4 * j + q;
@@ -39,24 +38,41 @@ __device__ __forceinline__ void sample_block(const SampleParams& p, int s, int i
       out[q] = fminf(fmaxf(v, p.lb[a]), p.ub[a]);
     }
   }
+}
+
+__device__ __forceinline__ void sample_block_to(const SampleParams& p, int s, int i, int j, float* dst_all) {
+  const int HA = p.H * p.A;
+  const long base = ((long)s * p.N + i) * HA + 4 * j;
+  float out[4];
+  sample_values4(p, s, i, j, out);
   if ((HA & 3) == 0) {
-    *reinterpret_cast<float4*>(p.out + base) = make_float4(out[0], out[1], out[2], out[3]);
+    *reinterpret_cast<float4*>(dst_all + base) = make_float4(out[0], out[1], out[2], out[3]);
   } else {
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      if (4 * j + q < HA) p.out[base + q] = out[q];
+      if (4 * j + q < HA) dst_all[base + q] = out[q];
   }
+}
+
+__device__ __forceinline__ void sample_block(const SampleParams& p, int s, int i, int j) {
+  sample_block_to(p, s, i, j, p.out);
+}
+
+// true when candidate i was sampled by this rank (its row is in the action buffer)
+__device__ __forceinline__ bool sampled_here(const SampleParams& p, int i) {
+  return p.n_cand == 0 || (i >= p.cand0 && i < p.cand0 + p.n_cand);
 }
 
 __global__ void __launch_bounds__(256) sample_actions_kernel(SampleParams p) {
   const int JB = (p.H * p.A + 3) >> 2;
-  const long total = (long)p.S * p.N * JB;
+  const int NC = p.n_cand ? p.n_cand : p.N;     // candidates this rank samples
+  const long total = (long)p.S * NC * JB;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
        idx += (long)gridDim.x * blockDim.x) {
     const int j = (int)(idx % JB);
-    const long si = idx / JB;                 // s * N + i
-    const int s = (int)(si / p.N);
-    const int i = (int)(si - (long)s * p.N);
+    const long si = idx / JB;                 // s * NC + local candidate
+    const int s = (int)(si / NC);
+    const int i = p.cand0 + (int)(si - (long)s * NC);
     if (p.active != nullptr && p.active[s] == 0) continue;
     sample_block(p, s, i, j);
   }
@@ -64,7 +80,7 @@ __global__ void __launch_bounds__(256) sample_actions_kernel(SampleParams p) {
 
 cudaError_t launch_sample_actions(const SampleParams& p, cudaStream_t st) {
   const int HA = p.H * p.A;
-  const long total = (long)p.S * p.N * ((HA + 3) / 4);
+  const long total = (long)p.S * (p.n_cand ? p.n_cand : p.N) * ((HA + 3) / 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
@@ -329,7 +345,15 @@ __global__ void __launch_bounds__(kSelectThreads) select_elites_kernel(SelectPar
   const float2 pr = load_pair(top);
   const float top_score = pair_score(p.objective, pr.x, pr.y, p.c_max);
   if (top_score > p.best_score[s]) {                       // cem_mpc.py:58 strict '>'
-    if (tid < p.A) p.best_action[s * p.A + tid] = p.actions[((long)s * N + top) * p.H * p.A + tid];
+    if (tid < p.A) {
+      if (p.regen && !sampled_here(p.sample, top)) {      // another rank sampled it: same counters, same row
+        float v[4];
+        sample_values4(p.sample, s, top, tid >> 2, v);
+        p.best_action[s * p.A + tid] = v[tid & 3];
+      } else {
+        p.best_action[s * p.A + tid] = p.actions[((long)s * N + top) * p.H * p.A + tid];
+      }
+    }
     __syncthreads();
     if (tid == 0) p.best_score[s] = top_score;
   }
@@ -508,7 +532,15 @@ select_elites_cluster_kernel(SelectParams p, int slice) {
     const float2 pr = load_pair(gbest_idx);
     const float top_score = pair_score(p.objective, pr.x, pr.y, p.c_max);
     if (top_score > p.best_score[s]) {                       // cem_mpc.py:58 strict '>'
-      if (tid < p.A) p.best_action[s * p.A + tid] = p.actions[((long)s * N + gbest_idx) * p.H * p.A + tid];
+      if (tid < p.A) {
+        if (p.regen && !sampled_here(p.sample, gbest_idx)) {   // another rank sampled it: same counters, same row
+          float v[4];
+          sample_values4(p.sample, s, gbest_idx, tid >> 2, v);
+          p.best_action[s * p.A + tid] = v[tid & 3];
+        } else {
+          p.best_action[s * p.A + tid] = p.actions[((long)s * N + gbest_idx) * p.H * p.A + tid];
+        }
+      }
       __syncthreads();
       if (tid == 0) p.best_score[s] = top_score;
     }
@@ -570,6 +602,16 @@ __device__ __forceinline__ void refit_body(const RefitParams& p, int s, const in
   const int tid = threadIdx.x;
   const float* acts = p.actions + (long)s * p.N * HA;
   const float kf = (float)p.K;
+  if (p.regen) {
+    // population sharding: elite rows that other ranks sampled are recomputed into the action buffer
+    // (same Philox counters, same mu / sigma => the owner's values bit for bit), then gathered as usual
+    const int JB = (HA + 3) >> 2;
+    for (int idx = tid; idx < p.K * JB; idx += kRefitThreads) {
+      const int e = elite[idx / JB];
+      if (!sampled_here(p.sample, e)) sample_block_to(p.sample, s, e, idx % JB, p.actions);
+    }
+    __syncthreads();
+  }
 
   const int c = tid % HA, grp = tid / HA;                  // HA <= 1024 (checked at creation)
   for (int pass = 0; pass < 2; ++pass) {
@@ -652,6 +694,16 @@ __global__ void __launch_bounds__(kRefitThreads) refit_cluster_kernel(RefitParam
   const int per = (p.K + kSelClusterSize - 1) / kSelClusterSize;
   const int k_lo = min(p.K, rank * per), k_hi = min(p.K, k_lo + per);
   const int c = tid % HA, grp = tid / HA;
+  if (p.regen) {
+    // population sharding: this CTA's elite rows that other ranks sampled are recomputed into the action
+    // buffer first (same counters, same mu / sigma => bit-identical); only this CTA reads them back
+    const int JB = (HA + 3) >> 2;
+    for (int idx = tid; idx < (k_hi - k_lo) * JB; idx += kRefitThreads) {
+      const int e = elite[k_lo + idx / JB];
+      if (!sampled_here(p.sample, e)) sample_block_to(p.sample, s, e, idx % JB, p.actions);
+    }
+    __syncthreads();
+  }
 
   for (int pass = 0; pass < 2; ++pass) {
     if (grp < groups) {

@@ -15,6 +15,10 @@ struct SampleParams {                 // cem_mpc.py:44-48
   int32_t iteration;
   const int32_t* active;
   float* out;                         // [S, N, H, A]
+  // Population sharding: a rank samples only the candidates it rolls out, [cand0, cand0 + n_cand)
+  // (n_cand = 0 means all N). Any rank can regenerate any candidate's row from (seed, iteration, i):
+  // selection and refit do that for the elite rows other ranks sampled (regen below).
+  int32_t cand0, n_cand;
 };
 
 struct ReduceParams {                 // mpc_policy.py:38-39, safe_cem_mpc.py:94-120
@@ -37,17 +41,21 @@ struct SelectParams {                 // cem_mpc.py:56-60
   float* out_scores;                  // [S, N] or null
   float* best_action;                 // [S, A]
   float* best_score;                  // [S]
+  int32_t regen;                      // the best candidate's row may not be in `actions`: recompute it
+  SampleParams sample;                // ... with this iteration's sampling parameters
 };
 
 struct RefitParams {                  // cem_mpc.py:61-67
   int32_t S, N, K, H, A;
   float smoothing, one_minus_smoothing, stddev_threshold;
-  const float* actions;
+  float* actions;
   const int32_t* elite;
   float* mu;
   float* sigma;
   int32_t* active;
   int32_t* iterations_run;
+  int32_t regen;                      // elite rows sampled by other ranks are recomputed into `actions` first
+  SampleParams sample;                // (same counters => bit-identical to the owner rank's rows)
 };
 
 struct FinalizeParams {               // cem_mpc.py:68
