@@ -106,3 +106,38 @@ def test_shard_bounds_and_errors():
     assert [shard_bounds(1024, 4, r) for r in range(4)] == [(0, 256), (256, 512), (512, 768), (768, 1024)]
     with pytest.raises(SimbaError):
         shard_bounds(150, 4, 0)
+
+
+class _FakeStatePolicy(object):
+    """Stands in for a CUDA policy built with n_states = S / world: what plan_states_sharded needs of it."""
+
+    def __init__(self, n_states):
+        self.n_states = n_states
+
+    def do_generate_action(self, states):
+        assert states.shape[0] == self.n_states and states.dtype == np.float32 and states.flags['C_CONTIGUOUS']
+        return np.stack([states[:, 0] * 2.0 + 1.0, states[:, 1] - states[:, 2]], 1).astype(np.float32), None
+
+
+def _state_sharded(rank, world, port, out_dir):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, 'ethz-safe-learning_b200')]
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from simba_b200 import distributed as sd
+    states = np.random.default_rng(5).normal(size=(12, 7))                # same on every rank (float64 on purpose)
+    acts = sd.plan_states_sharded(_FakeStatePolicy(12 // world), states)
+    np.save(os.path.join(out_dir, 'acts%d.npy' % rank), acts)
+    dist.destroy_process_group()
+
+
+def test_plan_states_sharded_gathers_in_state_order(tmp_path):
+    """BASELINE configs[3] at N > 1 (simba_b200.distributed.plan_states_sharded): every rank plans its
+    contiguous slice of the states, the actions come back in state order on every rank."""
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_state_sharded, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    states = np.random.default_rng(5).normal(size=(12, 7)).astype(np.float32)
+    want = np.stack([states[:, 0] * 2.0 + 1.0, states[:, 1] - states[:, 2]], 1).astype(np.float32)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / ('acts%d.npy' % r)), want)

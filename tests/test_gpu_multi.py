@@ -25,3 +25,4 @@ def test_population_sharded_plan_equals_single_gpu_plan():
     assert out.returncode == 0, out.stderr[-3000:]
     assert out.stdout.count("bit for bit on every rank: True") == 2
     assert "replicas identical: True" in out.stdout
+    assert "equal to the local plans: True" in out.stdout

@@ -38,6 +38,22 @@ def main():
             print("[%s] sharded(%d) == single-GPU plan, bit for bit on every rank: %s  action %s score %.6f"
                   % (precision, world, bool(t.item() > 0), a2, s2))
         ok = ok and bool(t.item() > 0)
+    # state sharding (BASELINE configs[3]): every rank plans its slice, all ranks get all actions
+    c = synthetic.make_workload('tiny', S=4)
+    states_all = synthetic.make_state(c['sensors'], seed=9, n_states=4 * world)
+    pol = synthetic.build_policy(c, 'penalty', precision='bf16', seed=5)
+    acts = sd.plan_states_sharded(pol, states_all)
+    lo, hi = sd.shard_bounds(4 * world, world, rank)
+    pol2 = synthetic.build_policy(c, 'penalty', precision='bf16', seed=5)
+    mine, _ = pol2.do_generate_action(states_all[lo:hi])
+    t = torch.from_numpy(acts).cuda()
+    ref = t.clone(); dist.broadcast(ref, 0)
+    good = torch.tensor([1.0 if (bool((ref == t).all()) and np.array_equal(acts[lo:hi], mine)) else 0.0], device='cuda')
+    dist.all_reduce(good, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("plan_states_sharded: %d states over %d ranks, same on every rank and equal to the local plans: %s"
+              % (4 * world, world, bool(good.item() > 0)))
+    ok = ok and bool(good.item() > 0)
     # C3 shape timing
     c = synthetic.make_workload('c3')
     pol = synthetic.build_policy(c, 'penalty', precision='bf16', member_map='particle', rank=rank, world_size=world, seed=3)
