@@ -11,6 +11,7 @@ Stated tolerance (external draws, C1 dims, H = 15):
 import numpy as np
 import pytest
 
+from oracle import simba_oracle as so
 from tests import helpers
 from tests.test_gpu_kernels import _oracle_rows, dev, P
 
@@ -80,7 +81,9 @@ def test_tc_plan_close_to_oracle_and_fp32(cfg, over):
           % (a16, a32, s16, s32, overlap, np.abs(mu16 - mu32).max()))
     assert np.all(np.isfinite(a16)) and np.isfinite(s16)
     assert abs(s16 - s32) < 5e-2
-    assert overlap >= 0.6
+    # measured overlaps of the final elite sets: 1.0 / 0.93 / 0.93 (after five refits on slightly different
+    # candidates); pinned 0.05-0.1 below the measurement instead of a loose 0.6
+    assert overlap >= 0.85
 
 
 def test_tc_philox_plan_runs_and_is_reproducible():
@@ -147,3 +150,86 @@ def test_tc_wide_batched_states_philox_and_early_exit():
     pol_e = helpers.cuda_policy(c, 'penalty', precision='bf16', stddev_threshold=0.9)
     pol_e.do_generate_action(c['state'], seed=11)
     assert np.all(pol_e.iterations_run == 1)
+
+
+def _bf16_iteration0(c, eps_transform=None):
+    """One CEM iteration's worth of per-candidate (return, cost) pairs from the bf16 kernel and from the
+    oracle on identical actions and draws (the same candidates are then comparable one by one; from the
+    second iteration on the two planners sample different candidates)."""
+    from simba_b200 import _lib
+    lib = _lib.load()
+    pol = helpers.cuda_policy(c, 'penalty', precision='bf16')
+    pl = pol._ensure_planner()
+    pl_o = helpers.oracle_planner(c, 'penalty')
+    rng = np.random.default_rng(12)
+    acts = np.clip(rng.standard_normal((c['N'], c['H'], c['A'])), -1, 1).astype(np.float32)   # iteration-0 sampling law
+    eps = rng.standard_normal((c['H'], c['P'] * c['N'], c['O'])).astype(np.float32)
+    B = c['P'] * c['N']
+    ret = torch.zeros(B, dtype=torch.float32, device='cuda')
+    mask = torch.zeros(B, dtype=torch.int64, device='cuda')
+    csum = torch.zeros(B, dtype=torch.float32, device='cuda')
+    pairs = torch.empty((c['N'], 2), dtype=torch.float32, device='cuda')
+    d_state, d_acts, d_eps = dev(c['state'][None]), dev(acts[None]), dev(eps[None])
+    _lib.check(lib.simba_rollout_score(pl, P(d_state), P(d_acts), P(d_eps), 0, 0, None, P(ret), P(mask), P(csum), None))
+    _lib.check(lib.simba_score_reduce(pl, P(ret), P(mask), P(csum), None, P(pairs), None))
+    torch.cuda.synchronize()
+    eps_o = eps if eps_transform is None else eps_transform(eps)
+    traj, cum0, mask0, csum0 = _oracle_rows(c, pl_o, acts, eps_o, 'penalty')
+    acts_b = np.tile(acts, (c['P'], 1, 1))
+    ret_o, counts_o, safe_o = pl_o.objective_safe(traj, acts_b)
+    return pairs.cpu().numpy(), ret_o, counts_o, safe_o
+
+
+def _bf16_round(x):
+    """round-to-nearest-even to bfloat16, as the kernel's cvt.rn.bf16x2.f32 does"""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def test_tc_elite_classification_is_margin_aware_exact_vs_oracle():
+    """bf16 kernel vs the ORACLE (not vs the fp32 kernel) at C1 dims: every candidate whose oracle score is
+    more than 2e-2 away from the K-th best score must land on the same side of the elite cut; the safety
+    decision must agree wherever the particle count is not at the threshold; the overlap of the two elite
+    sets is pinned to what was measured (14 of 15 at this seed: the odd one out sits within the margin of the
+    cut) minus 0.05 instead of a loose 0.6."""
+    c = helpers.workload('c1')
+    pairs, ret_o, counts_o, safe_o = _bf16_iteration0(c)
+    c_max = so.beta_count_threshold(c['P'], 0.15)
+    score_o = ret_o - (~safe_o).astype(np.float32) * np.float32(100)
+    score_d = pairs[:, 0] - (pairs[:, 1] > c_max).astype(np.float32) * np.float32(100)
+    K = c['K']
+    order_o = np.argsort(-score_o, kind='stable')
+    kth = score_o[order_o[K - 1]]
+    elite_o = set(order_o[:K].tolist())
+    elite_d = set(np.argsort(-score_d, kind='stable')[:K].tolist())
+    clear = np.abs(score_o - kth) > 2e-2                      # decisively inside / outside the elite set
+    wrong = [i for i in np.nonzero(clear)[0] if (i in elite_o) != (i in elite_d)]
+    overlap = len(elite_o & elite_d) / float(K)
+    # safety: identical wherever the violating-particle count is not exactly at / next to the threshold
+    decisive = np.abs(counts_o - (c_max + 0.5)) > 1.0
+    safe_d = pairs[:, 1] <= c_max
+    print("bf16 vs oracle, iteration 0: elite overlap %.3f, %d of %d candidates decisive, %d misclassified; "
+          "max|dret| %.4g; safety flips among decisive %d"
+          % (overlap, int(clear.sum()), c['N'], len(wrong), np.abs(pairs[:, 0] - ret_o).max(),
+             int((safe_d[decisive] != safe_o[decisive]).sum())))
+    assert not wrong
+    assert np.array_equal(safe_d[decisive], safe_o[decisive])
+    assert np.max(np.abs(pairs[:, 0] - ret_o)) < 2e-2
+    assert overlap >= 0.88
+
+
+def test_tc_bf16_rounded_noise_effect_on_returns_is_bounded():
+    """The bf16 rollout consumes its N(0,1) draws rounded to bf16. Bound what that
+    does to the per-candidate mean return: the oracle fed with the bf16-rounded draws vs the oracle fed
+    with the fp32 draws differ by far less than the bf16 tolerance, and the kernel is at least as close to
+    the rounded-draw oracle as to the plain one."""
+    c = helpers.workload('c1')
+    pairs, ret_plain, _, _ = _bf16_iteration0(c)
+    _, ret_rounded, _, _ = _bf16_iteration0(c, eps_transform=_bf16_round)
+    shift = np.abs(ret_rounded - ret_plain)
+    print("bf16-rounded draws: mean |d mean return| %.3g, max %.3g; kernel vs rounded-draw oracle max %.3g, vs plain %.3g"
+          % (shift.mean(), shift.max(), np.abs(pairs[:, 0] - ret_rounded).max(), np.abs(pairs[:, 0] - ret_plain).max()))
+    # measured: mean 1.3e-4, max 7.7e-3 (one done / cost threshold flip in one of a candidate's 20 rows)
+    assert shift.max() < 2e-2 and shift.mean() < 5e-4
+    assert np.abs(pairs[:, 0] - ret_rounded).mean() <= np.abs(pairs[:, 0] - ret_plain).mean() + 1e-4
