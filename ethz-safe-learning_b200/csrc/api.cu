@@ -605,6 +605,7 @@ struct simba_planner {
   float* h_out = nullptr;              // pinned: [S*A action][S score][S iters(int)]
   const float *ext_z_actions = nullptr, *ext_eps = nullptr, *ext_z_final = nullptr;
   cudaStream_t own_stream = nullptr;
+  cudaEvent_t plan_done = nullptr;   // recorded after every plan: the next plan (any stream) waits on it
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   int launches_per_plan = 0;
@@ -657,6 +658,7 @@ static void planner_free(simba_planner* p) {
   if (p->graph) cudaGraphDestroy(p->graph);
   if (p->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(p->comm);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
+  if (p->plan_done) cudaEventDestroy(p->plan_done);
   cudaFree(p->d_tiles); cudaFree(p->actions); cudaFree(p->row_ret); cudaFree(p->row_csum);
   cudaFree(p->pairs_local); cudaFree(p->pairs_all); cudaFree(p->mu); cudaFree(p->sigma);
   cudaFree(p->best_action); cudaFree(p->best_score); cudaFree(p->scores); cudaFree(p->row_cmask); cudaFree(p->key_scratch);
@@ -772,7 +774,8 @@ extern "C" int simba_planner_create(simba_model_t* model, const simba_planner_co
                  cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMallocHost((void**)&p->h_seed_ring, 64 * sizeof(uint64_t)) != cudaSuccess ||
       cudaMallocHost((void**)&p->h_out, S * (A + 2) * 4) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->plan_done, cudaEventDisableTiming) != cudaSuccess) {
     planner_free(p); delete p;
     return fail(SIMBA_ERR_CUDA, "planner staging allocation failed: %s",
                 cudaGetErrorString(cudaGetLastError()));
@@ -1116,7 +1119,8 @@ static int ensure_graph(simba_planner* p) {
 }
 
 // stage the seed in a pinned ring slot and copy it to the device ahead of the graph (up to 64
-// un-synchronised plans may be in flight per planner)
+// un-synchronised plans may be queued per planner; they execute one after the other: the plan entry
+// points chain them with an event even across streams)
 static int upload_seed(simba_planner* p, uint64_t seed, cudaStream_t st) {
   uint64_t* slot = p->h_seed_ring + (p->seed_slot++ & 63);
   *slot = seed;
@@ -1139,6 +1143,9 @@ extern "C" int simba_plan(simba_planner_t* p, const float* states, uint64_t seed
   const size_t S = p->cfg.n_states, O = p->model->cfg.obs_dim, A = p->model->cfg.act_dim;
   int rc = ensure_graph(p);
   if (rc != SIMBA_OK) return rc;
+  // a planner owns ONE workspace (seed, states, mu / sigma, actions, outputs): plans issued on different
+  // streams are serialised behind each other here (a no-op when the caller keeps to one stream)
+  if (p->plan_done) CUDA_TRY(cudaStreamWaitEvent(st, p->plan_done, 0));
   rc = upload_seed(p, seed, st);
   if (rc != SIMBA_OK) return rc;
   if (states != p->d_states)
@@ -1150,6 +1157,7 @@ extern "C" int simba_plan(simba_planner_t* p, const float* states, uint64_t seed
     CUDA_TRY(cudaMemcpyAsync(out_score, p->d_out_score, S * 4, cudaMemcpyDeviceToDevice, st));
   if (out_iterations && out_iterations != p->d_out_iters)
     CUDA_TRY(cudaMemcpyAsync(out_iterations, p->d_out_iters, S * 4, cudaMemcpyDeviceToDevice, st));
+  if (p->plan_done) CUDA_TRY(cudaEventRecord(p->plan_done, st));
   return SIMBA_OK;
 }
 
@@ -1162,6 +1170,7 @@ extern "C" int simba_plan_host(simba_planner_t* p, const float* states_host, uin
   cudaStream_t st = p->own_stream;
   int rc = ensure_graph(p);
   if (rc != SIMBA_OK) return rc;
+  if (p->plan_done) CUDA_TRY(cudaStreamWaitEvent(st, p->plan_done, 0));    // behind a plan_device() on another stream
   rc = upload_seed(p, seed, st);
   if (rc != SIMBA_OK) return rc;
   CUDA_TRY(cudaMemcpyAsync(p->d_states, states_host, S * O * 4, cudaMemcpyHostToDevice, st));

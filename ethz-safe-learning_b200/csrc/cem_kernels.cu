@@ -157,6 +157,7 @@ cudaError_t launch_score_reduce(const ReduceParams& p, cudaStream_t st) {
 // summation order — and therefore mu/sigma — bit-identical on every rank.
 // =============================================================================================
 __device__ __forceinline__ uint32_t ordered_u32(float f) {
+  if (f != f) return 0u;                          // NaN (a diverged rollout) ranks below every number: never elite
   f = f + 0.0f;                                   // -0 -> +0 so that -0 == +0 ties by index
   const uint32_t u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);

@@ -256,7 +256,10 @@ class MlpEnsemble(object):
 
     def training_step(self, inputs, targets):
         """mlp_ensemble.py:134-146. inputs [E, B, in], targets [E, B, out] -> loss (0-dim CUDA
-        tensor; float(loss) synchronises)."""
+        tensor; float(loss) synchronises). B may be anything up to the `batch_size` the ensemble was
+        constructed with (the trainer's workspace is sized once for it; the reference accepts any B —
+        construct the ensemble with the largest batch you will pass, a larger one raises SimbaError
+        SIMBA_ERR_SHAPE)."""
         t = self._ensure_trainer()
         x, _ = _device.to_device(inputs)
         y, _ = _device.to_device(targets)

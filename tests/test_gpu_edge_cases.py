@@ -214,3 +214,53 @@ def test_handles_release_their_device_memory():
         cycle()
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < 32 * 1024 * 1024, (free0, free1)
+
+
+def test_nan_scored_candidates_are_never_elite():
+    """A diverged rollout gives a NaN mean return; such candidates must rank below every finite score
+    (they used to rank above +inf and fill the elite set)."""
+    import ctypes as C
+    from simba_b200 import _lib
+    lib = _lib.load()
+    c = helpers.workload('tiny')
+    pol = helpers.cuda_policy(c, 'reward', precision='fp32')
+    pl = pol._ensure_planner()
+    N, K, H, A = c['N'], c['K'], c['H'], c['A']
+    rng = np.random.default_rng(4)
+    pairs = np.zeros((N, 2), np.float32)
+    pairs[:, 0] = rng.normal(0, 1, N)
+    bad = [0, 3, 7, N - 1]
+    pairs[bad, 0] = np.nan
+    acts = rng.uniform(-1, 1, (1, N, H, A)).astype(np.float32)
+    d_pairs, d_acts = torch.from_numpy(pairs).cuda(), torch.from_numpy(acts).cuda()
+    elite = torch.empty((K,), dtype=torch.int32, device='cuda')
+    best_a = torch.zeros((A,), dtype=torch.float32, device='cuda')
+    best_s = torch.full((1,), -np.inf, dtype=torch.float32, device='cuda')
+    P = lambda t: C.c_void_p(t.data_ptr())
+    _lib.check(lib.simba_select_elites(pl, P(d_pairs), P(d_acts), None, P(elite), None, P(best_a), P(best_s), None))
+    torch.cuda.synchronize()
+    got = set(elite.cpu().numpy().tolist())
+    finite = np.where(np.isfinite(pairs[:, 0]))[0]
+    want = set(finite[np.argsort(-pairs[finite, 0], kind='stable')[:K]].tolist())
+    assert got == want and not (got & set(bad))
+    assert np.isfinite(float(best_s.cpu()[0]))
+
+
+def test_plans_on_two_streams_share_one_planner_safely():
+    """plan_device() on two different torch streams and generate_action() on the planner's own stream use
+    one workspace: the library chains them with an event, so the results equal the serial ones."""
+    c = helpers.workload('tiny')
+    pol = helpers.cuda_policy(c, 'penalty', precision='bf16')
+    st = torch.from_numpy(np.ascontiguousarray(c['state'])[None]).cuda()
+    ref = [pol.plan_device(st, seed=s)[0].clone() for s in (3, 4, 5)]
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for k, (seed, stream) in enumerate(((3, s1), (4, s2), (5, s1))):
+        with torch.cuda.stream(stream):
+            oa = torch.empty((1, c['A']), dtype=torch.float32, device='cuda')
+            pol.plan_device(st, seed, oa)
+            outs.append(oa)
+    torch.cuda.synchronize()
+    for a, b in zip(ref, outs):
+        assert torch.equal(a, b)
