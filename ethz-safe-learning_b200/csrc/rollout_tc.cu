@@ -435,15 +435,7 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
 #else
             z = philox_noise8_bf16(key, (uint32_t)(o0 >> 3), row32, (uint32_t)t | c2_base, c3_noise);
 #endif
-            if (o0 + 8 > O) {                               // padded outputs draw nothing (their delta is 0)
-              uint32_t w[4] = {z.x, z.y, z.z, z.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (o0 + 2 * i >= O) w[i] = 0u;
-                else if (o0 + 2 * i + 1 >= O) w[i] &= 0xffffu;
-              }
-              z = make_uint4(w[0], w[1], w[2], w[3]);
-            }
+            if (o0 + 8 > O) z = mask_noise8(z, o0, O);      // padded outputs draw nothing (their delta is 0)
           }
           noise.put4_dyn(b, z);
         };
@@ -453,6 +445,7 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
         publish_a();                                        // layer-0 input of step 0
         named_bar_arrive_n(kBarPart + j, tile_bar_threads);  // partial minima of s_0 published (scorer warp)
 
+        PhiloxState ps{0u, 0u, 0u, 0u, 0u, 0u};             // a noise block in flight across two layers (latency variant)
         for (int t = 0; t < H; ++t) {
 #ifdef SIMBA_TC_TIMELINE
           tl_t = t;
@@ -483,10 +476,27 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
             publish_a();
             TL(3 + l * 4);
             if (prm.sampling_propagation) {
-              // the NB Philox blocks of the step, one per hidden layer (the last layer takes the rest)
-              if (l < NB) make_noise(l, t);
-              if (l == L - 1)
-                for (int b = L; b < NB; ++b) make_noise(b, t);
+              if (NTILES == 1 && L >= 2 * NB && eps_row == nullptr) {
+                // latency variant: a whole block (~1.3 k cycles for a lone warp: two serial dependency
+                // chains) is longer than one layer's MMA shadow, so it is split over two layers — the ten
+                // Philox rounds after an even layer, Box-Muller after the following odd one
+                const int b = l >> 1, o0 = hc.o_base + b * 8;
+                if (b < NB && o0 < O) {
+                  if ((l & 1) == 0) {
+                    ps = PhiloxState{(uint32_t)(o0 >> 3), row32, (uint32_t)t | c2_base, c3_noise, key.x, key.y};
+                    philox_rounds<10>(ps);
+                  } else {
+                    uint4 z = philox_finish_noise8_bf16(ps);
+                    if (o0 + 8 > O) z = mask_noise8(z, o0, O);
+                    noise.put4_dyn(b, z);
+                  }
+                }
+              } else {
+                // the NB Philox blocks of the step, one per hidden layer (the last layer takes the rest)
+                if (l < NB) make_noise(l, t);
+                if (l == L - 1)
+                  for (int b = L; b < NB; ++b) make_noise(b, t);
+              }
             }
             TL(4 + l * 4);
           }

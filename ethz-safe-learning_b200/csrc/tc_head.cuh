@@ -63,6 +63,17 @@ __device__ __forceinline__ uint4 philox_noise8_bf16(uint2 key, uint32_t c0, uint
   return philox_finish_noise8_bf16(p);
 }
 
+// zero the draws of padded outputs (o >= O) of the block that starts at output o0
+__device__ __forceinline__ uint4 mask_noise8(uint4 z, int o0, int O) {
+  uint32_t w[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (o0 + 2 * i >= O) w[i] = 0u;
+    else if (o0 + 2 * i + 1 >= O) w[i] &= 0xffffu;
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // externally supplied draws (parity mode): 8 consecutive floats of one row, zero beyond O
 __device__ __forceinline__ uint4 external_noise8_bf16(const float* ep, int o0, int O) {
   float z[8];
