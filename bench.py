@@ -170,7 +170,7 @@ def time_cpu_planner(c, budget_s=20.0, max_plans=12, label="C1"):
             "sample": "%d whole %s plans on the %s fp32 restatement of the TensorFlow reference (the faster of "
                       "the two restatements here: %s), threads=%d of %d host cpus; median %.1f ms, best %.1f ms per plan"
                       % (len(times), label, best_name,
-                         ", ".join("%s %.0f ms" % kv for kv in sorted(probe.items())), threads, os.cpu_count(),
+                         ", ".join("%s %.0f ms" % (k, v * 1e3) for k, v in sorted(probe.items())), threads, os.cpu_count(),
                          med * 1e3, best * 1e3),
             "transitions_per_s": n * c['H'] * c['P'] * c['N'] / med, "ms_per_plan_median": med * 1e3}
 

@@ -1,12 +1,18 @@
 """TEST INFRASTRUCTURE ONLY — CPU restatement of the reference's CEM-MPC planning call.
 
-PARITY UNPINNED: the reference (yardenas/ethz-safe-learning, "simba") ships no tests, golden
-vectors or fixtures, and TensorFlow / TensorFlow-Probability / gym / safety_gym are not
-installable in this environment (no wheels, no network), so the reference itself cannot be
-run. This file restates the reference's algorithm op for op in numpy, following the TensorFlow
-documentation for each stock op, and is pinned only by known-answer tests derived from the
-reference's formulas (tests/test_oracle.py). Only tests/, __graft_entry__.smoke() and
-bench.py's cpu_baseline / --impl reference legs may import it; the product never does.
+PINNED TO THE REFERENCE'S OWN CODE, with one stated limit. The reference (yardenas/ethz-safe-learning,
+"simba") ships no tests, golden vectors or fixtures, and TensorFlow / TensorFlow-Probability / gym /
+safety_gym are not installable here (no wheels, no network). The pin is therefore made by executing
+the UNMODIFIED reference sources (CemMpc / SafeCemMpc.do_generate_action, TransitionModel,
+MlpEnsemble, SafetyGymStateScorer) over a torch-backed stand-in for the TensorFlow ops they call
+(tests/golden/ref_shim.py, generator tests/golden/make_reference_golden.py): the committed
+tests/golden/reference_*.npz hold what the reference's control flow, shapes, masks and reductions
+produce on our workloads, and tests/test_reference_golden.py holds this file to them. What remains
+unpinned is only the arithmetic INSIDE each stock TF op (softplus' range switch, top_k tie order,
+moments), restated from the TensorFlow documentation and checked by known-answer tests
+(tests/test_oracle.py). oracle/torch_ref.py is a second, differently structured restatement
+held to this one at 1e-6 (tests/test_torch_ref.py). Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may import this file; the product never does.
 
 Every function cites the reference file:line (relative to the reference repo root) it follows.
 All arithmetic runs in `dtype` (float32 = the reference's type; float64 = shadow used by the

@@ -1,5 +1,6 @@
-"""Regenerates tests/golden/oracle_tiny_plan.npz from the CPU oracle (self-golden; the reference has
-no fixtures and cannot be imported here: TensorFlow / TFP / gym are not installed).
+"""Regenerates tests/golden/oracle_tiny_plan.npz from the CPU oracle: a self-golden that freezes the
+oracle's per-iteration trace (all four objectives, incl. the two the reference only has as dead code).
+The fixtures produced by the reference's own code are reference_*.npz (make_reference_golden.py).
 Run from the repo root:  python tests/golden/make_golden.py"""
 import os
 import sys
