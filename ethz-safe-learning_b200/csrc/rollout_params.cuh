@@ -29,6 +29,7 @@ struct RolloutParams {
   const void* bias_k16;       // [E][L+1][4096 B] bias K-blocks (see simba_model_commit)
   const float* bias_tc;       // [E][L+1][128] fp32 (heads: mu bias at [0, O), var bias at [64, 64+O))
   int32_t tc_tiles_per_cta;   // 1 (latency: small populations) or 2 (MMA / epilogue ping-pong)
+  int32_t tc_pair;            // one-tile variant only: a cluster of two CTAs per tile splits the head pass
   int32_t pdl;                // launch with programmatic stream serialization (fused plan path)
   float tc_scale_a[64];       // bf16 path: x_scaled[k] = fma(x[k], a[k], b[k]); zero beyond O + A
   float tc_scale_b[64];
@@ -67,6 +68,7 @@ cudaError_t launch_rollout_f32(const RolloutParams& prm, int n_tiles, cudaStream
 cudaError_t launch_rollout_tc(const RolloutParams& prm, int n_tiles, cudaStream_t stream);
 bool rollout_tc_supported(int O, int A, int L, int U, int H);
 bool rollout_tc_two_tiles_fit(int L, int n_constraints);
+bool rollout_tc_pair_fits(int L, int n_constraints);
 cudaError_t launch_rollout_tc_wide(const RolloutParams& prm, int n_tiles, cudaStream_t stream);
 bool rollout_tc_wide_supported(int O, int A, int L, int U, int H);
 bool rollout_tc_wide_fits(int L, int U, int n_constraints);

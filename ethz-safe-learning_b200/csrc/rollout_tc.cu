@@ -100,16 +100,46 @@ struct AStoreTmem {
   }
 };
 
+// PAIR variant: the slice also goes into the peer CTA's exchange buffer (one 16-byte slot per thread
+// and step parity; the peer's thread of the same row and column group moves it into its own A operand)
+struct AStorePair {
+  uint32_t t_a;
+  uint32_t peer_slot;     // shared::cluster address of this thread's slot in the peer's buffer 0
+  uint32_t buf_off;       // byte offset of the current step's buffer
+  uint32_t peer_bar;      // shared::cluster address of the peer's mbarrier of the current step
+  __device__ __forceinline__ void store8(int k0, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3) const {
+    const uint32_t pk[4] = {p0, p1, p2, p3};
+    tmem_st<4>(t_a + (uint32_t)(k0 >> 1), pk);
+    st_async_v4(peer_slot + buf_off, p0, p1, p2, p3, peer_bar);
+  }
+};
+
 }  // namespace
 
 // NTILES row tiles per CTA, Q epilogue threads per rollout row.
-template <int NTILES, int Q>
+//
+// PAIR (latency variant for plans with at most half as many tiles as SMs): a CLUSTER OF TWO CTAs works
+// on one row tile. The hidden layers are computed redundantly by both (no exchange, no extra latency:
+// the SMs would be idle otherwise); the Gaussian-head / state pass — the longest single stage of a step,
+// bound by the SM's MUFU rate — is split by output columns: CTA c owns state dims [32 c, 32 c + 32),
+// its threads push their 8 scaled bf16 inputs of the next step into the peer's shared memory (DSMEM)
+// as well as into their own A operand, and their partial lidar minima into CTA 0's exchange buffer, with
+// st.async: each store completes its bytes on an mbarrier of the destination CTA, which that CTA's scorer
+// warp arms with the step's byte count (expect_tx), so there is no fence and no arrive on the producer
+// side. The receiving thread waits for the phase, moves its row's 16 bytes into the A operand and
+// publishes it. Exchange buffers and their mbarriers alternate by step parity; buffer p of step t + 2 is
+// written only after the peer has sent all of step t + 1, which it does after consuming step t, so two
+// suffice (and a barrier is re-armed for step t + 2 long before that step's bytes can arrive; were they
+// early, a negative transaction count is legal and the pending arm keeps the phase open).
+template <int NTILES, int Q, bool PAIR>
 __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const RolloutParams prm) {
+  static_assert(!PAIR || (NTILES == 1 && Q == 4), "the pair variant is the one-tile latency configuration");
   constexpr int kTileThreads = Q * 128;
   constexpr int kTileWarps = Q * 4;
   constexpr int kEpiThreads = NTILES * kTileThreads;
   constexpr int kEpiWarps = kEpiThreads / 32;
-  constexpr int OW = 64 / Q;          // head outputs (= state dims = layer-0 K elements) per thread
+  constexpr int OW = (PAIR ? 32 : 64) / Q;   // head outputs (= state dims = layer-0 K elements) per thread
+  constexpr int NSL = PAIR ? 2 * Q : Q;      // column slices of a row's head outputs (one partial minimum each)
   constexpr int NB = OW / 8;          // Philox blocks / 8-wide chunks per thread and step
   constexpr int HCOLS = 128 / Q;      // accumulator columns per thread and hidden layer
   // TMEM columns per tile: 128 fp32 accumulator columns, 64 fp32 state columns and 64 columns that
@@ -126,6 +156,8 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
   const int H = g.H;
   const int O = g.O, A = g.A;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;            // CTA within the pair
+  const int cta_tile0 = (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x) * NTILES;
   const bool l0_pad_bias = (O + A + 2 <= 64);     // layer-0 bias rides in the K padding (see pack in api.cu)
   constexpr int n_quarters = 4;                   // TMEM lane quarters (= warps per column group) of a tile
   constexpr int tile_bar_threads = Q * 128 + 32;  // a tile's epilogue warps + one partner warp (issuer / scorer)
@@ -138,27 +170,60 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
   float* scale_smem = reinterpret_cast<float*>(ones_smem + 4096);          // [2][64]: a, b of x*a+b
   float* pen_smem = scale_smem + 128;                                      // [kHeadParts][64]
   const int nparts = 1 + prm.scorer.n_constraints;                         // goal + constrained lidars
-  float* part_smem = pen_smem + kHeadParts * 64;                           // [NTILES][Q][nparts][128]
-  uint4* noise_smem = reinterpret_cast<uint4*>(part_smem + NTILES * Q * nparts * 128);   // [NB][threads]
+  float* part_smem = pen_smem + kHeadParts * 64;                           // [1 or 2 (PAIR)][NTILES][NSL][nparts][128]
+  const int part_buf_floats = NTILES * NSL * nparts * 128;
+  uint4* xch_smem = reinterpret_cast<uint4*>(part_smem + (PAIR ? 2 : 1) * part_buf_floats);   // PAIR: [2][Q][128] x 16 B
+  uint4* noise_smem = xch_smem + (PAIR ? 2 * Q * 128 : 0);                                    // [NB][threads]
   // running objective of every rollout row (RowScore fields, field-major), kept by the tile's scorer warp
   uint32_t* rs_smem = reinterpret_cast<uint32_t*>(noise_smem + (kPark ? NB * kEpiThreads : 0));   // [NTILES][8][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(rs_smem + NTILES * 8 * 128);
   // bars[0] = weights landed; bars[1 + j] = MMAs of tile j committed. Named barriers: 0 = CTA, 1 = all
   // epilogue threads, 2 + j = "accumulator ready" of tile j, 2 + NTILES + j = "A ready"
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + NTILES);
+  // PAIR: bars[1 + NTILES + p] = the peer's warps have sent their step-parity-p slices
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + NTILES + 2);
   TileInfo* tinfo = reinterpret_cast<TileInfo*>(tmem_slot + 2);
   uint64_t* seed_sh = reinterpret_cast<uint64_t*>(tinfo + NTILES);
 
   const uint32_t bar_w = smem_u32(&bars[0]);
 
   pdl_launch_dependents();
+  // member whose weights this CTA stages (-1: no rows at all); fixed geometry, readable before the PDL wait
+  auto cta_member = [&]() {
+    int wm = -1;
+    for (int q = 0; q < NTILES; ++q)
+      if (cta_tile0 + q < prm.n_tiles && prm.tiles[cta_tile0 + q].count > 0) wm = prm.tiles[cta_tile0 + q].member;
+    return wm;
+  };
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
 #pragma unroll
     for (int j = 0; j < NTILES; ++j) {
       mbar_init(smem_u32(&bars[1 + j]), 1);                      // tcgen05.commit
     }
+    if (PAIR) {                                                  // armed below, once the tile is known to be live
+      mbar_init(smem_u32(&bars[1 + NTILES]), 1);
+      mbar_init(smem_u32(&bars[2 + NTILES]), 1);
+    }
     fence_barrier_init();
+    // The member's weights do not depend on the previous kernel (the tile list is fixed geometry), so
+    // their TMA copies start before the programmatic-dependency wait and overlap the CEM update's tail:
+    // one bulk copy per layer, all onto bars[0]. A CTA whose tiles turn out inactive still drains them.
+    {
+      const int wm = cta_member();
+      if (wm >= 0) {
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(prm.w_bf16) + (size_t)wm * prm.w_bf16_member_bytes;
+        const uint32_t bk_bytes = (uint32_t)(L + 1) * 4096u;
+        mbar_expect_tx(bar_w, w_bytes + bk_bytes);
+        uint32_t off = 0;
+        for (int l = 0; l <= L; ++l) {
+          const uint32_t nb = (l == 0) ? kAtomBytes : 2 * kAtomBytes;
+          bulk_g2s(smem_u32(w_smem + off), wsrc + off, nb, bar_w);
+          off += nb;
+        }
+        bulk_g2s(smem_u32(biask_smem), reinterpret_cast<const uint8_t*>(prm.bias_k16) + (size_t)wm * bk_bytes,
+                 bk_bytes, bar_w);
+      }
+    }
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   // everything above is independent of the previous kernel (the CEM update that wrote the actions
@@ -166,7 +231,7 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
   pdl_wait_prior_grid();
   if (threadIdx.x == 0) *seed_sh = prm.seed_ptr ? *prm.seed_ptr : prm.seed;
   if (threadIdx.x < NTILES) {
-    const int ti = blockIdx.x * NTILES + threadIdx.x;
+    const int ti = cta_tile0 + threadIdx.x;
     TileInfo info{0, 0, 0, 0};
     if (ti < prm.n_tiles) {
       const Tile t = prm.tiles[ti];
@@ -181,16 +246,23 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
     }
     tinfo[threadIdx.x] = info;
   }
+  if (PAIR && threadIdx.x == 0) {
+    // arm the exchange barriers for s_0 (step -1, barrier 1) and step 0 (barrier 0); see the scorer warps
+    const uint32_t per_step = crank == 0 ? (uint32_t)(kEpiThreads * 4 * nparts) : 0u;
+    mbar_expect_tx(smem_u32(&bars[2 + NTILES]), per_step + (uint32_t)(kEpiThreads * 16));
+    const uint32_t b0 = per_step + (1 < H ? (uint32_t)(kEpiThreads * 16) : 0u);
+    if (b0 != 0u) mbar_expect_tx(smem_u32(&bars[1 + NTILES]), b0);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                                 // the peer's mbarriers are armed before any store can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   bool any_valid = false;
-  int member = 0;
 #pragma unroll
   for (int j = 0; j < NTILES; ++j)
-    if (tinfo[j].valid) { any_valid = true; member = tinfo[j].member; }
+    if (tinfo[j].valid) any_valid = true;
 
   if (any_valid) {
     if (warp >= kEpiWarps + NTILES) {
@@ -203,14 +275,28 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
       // next head pass overwrites the exchange buffer.
       const int j = warp - kEpiWarps - NTILES;
       const TileInfo tis = tinfo[j];
-      if (tis.valid) {
+      // PAIR: bytes the peer sends into this CTA for step t — CTA 1's partial minima go to CTA 0 every step,
+      // the 16-byte next-input slices go both ways whenever a next step follows
+      auto xbytes = [&](int t) -> uint32_t {
+        return (crank == 0 ? (uint32_t)(kEpiThreads * 4 * nparts) : 0u) + (t + 1 < H ? (uint32_t)(kEpiThreads * 16) : 0u);
+      };
+      const uint32_t xbar = smem_u32(&bars[1 + NTILES]);
+      if (PAIR && tis.valid && crank != 0) {
+        // CTA 1 keeps no objective: its scorer warp only re-arms the two exchange barriers, each for the
+        // step after next once the current one has completed
+        for (int ts = -1; ts + 1 < H; ++ts) {
+          mbar_wait(xbar + 8u * ((uint32_t)ts & 1u), (uint32_t)((ts + 1) >> 1) & 1u);
+          if (lane == 0 && xbytes(ts + 2) != 0u) mbar_expect_tx(xbar + 8u * ((uint32_t)ts & 1u), xbytes(ts + 2));
+        }
+      }
+      if (tis.valid && crank == 0) {                                       // PAIR: CTA 0 keeps the objective
         const simba_scorer_t& sc = prm.scorer;
         const bool done_first = objective_done_first(prm.objective);
         // the objective of the lane's four rows is parked in shared memory (field-major), so the row
         // loop stays rolled: this warp is never on the critical path and the kernel already exceeds the
         // instruction cache
         uint32_t* my_rs = rs_smem + j * 8 * 128 + lane;                    // [8 fields][128 rows]
-        const float* part_tile = part_smem + (j * Q * nparts) * 128;       // [Q][nparts][128 rows]
+        const float* part_tile0 = part_smem + (j * NSL * nparts) * 128;    // [NSL][nparts][128 rows]
 #pragma unroll 1
         for (int i = 0; i < n_quarters; ++i) {
           const int row = lane + 32 * i;
@@ -220,11 +306,17 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
         }
         for (int ts = -1; ts < H; ++ts) {                                  // ts = -1: distance / cost of s_0
           named_bar_sync_n(kBarPart + j, tile_bar_threads);
+          const float* part_tile = part_tile0;
+          if (PAIR) {                                                      // + the peer CTA's slices of this step
+            mbar_wait(xbar + 8u * ((uint32_t)ts & 1u), (uint32_t)((ts + 1) >> 1) & 1u);
+            if (lane == 0 && ts + 2 < H) mbar_expect_tx(xbar + 8u * ((uint32_t)ts & 1u), xbytes(ts + 2));
+            part_tile += (ts & 1) * part_buf_floats;
+          }
 #pragma unroll 1
           for (int i = 0; i < n_quarters; ++i) {
             uint32_t* q = my_rs + 32 * i;
             float nd, nc;
-            head_combine<Q>(sc, part_tile + lane + 32 * i, nparts, nd, nc);
+            head_combine<NSL>(sc, part_tile + lane + 32 * i, nparts, nd, nc);
             if (ts < 0) {
               q[4 * 128] = __float_as_uint(nd);
               q[5 * 128] = __float_as_uint(nc);
@@ -265,21 +357,6 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
       // ====================== MMA issuer warp of tile j (lane 0 issues; the warp stays converged) ==============
       const int j = warp - kEpiWarps;
       if (tinfo[j].valid) {
-        if (lane == 0 && (j == 0 || !tinfo[0].valid)) {
-          // weights of this member: one TMA bulk copy per layer, all onto bars[0]
-          const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(prm.w_bf16) +
-                                (size_t)member * prm.w_bf16_member_bytes;
-          const uint32_t bk_bytes = (uint32_t)(L + 1) * 4096u;
-          mbar_expect_tx(bar_w, w_bytes + bk_bytes);
-          uint32_t off = 0;
-          for (int l = 0; l <= L; ++l) {
-            const uint32_t nb = (l == 0) ? kAtomBytes : 2 * kAtomBytes;
-            bulk_g2s(smem_u32(w_smem + off), wsrc + off, nb, bar_w);
-            off += nb;
-          }
-          bulk_g2s(smem_u32(biask_smem), reinterpret_cast<const uint8_t*>(prm.bias_k16) + (size_t)member * bk_bytes,
-                   bk_bytes, bar_w);
-        }
         const uint32_t bar_acc = smem_u32(&bars[1 + j]);
         const uint32_t d_tmem = tmem_base + (uint32_t)j * 128;
         const uint32_t a_tmem = tmem_base + (uint32_t)(NTILES * 192 + j * 64);       // lane 0, A columns
@@ -357,14 +434,43 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
         HeadCtx hc;
         hc.t_acc = t_acc;
         hc.t_state = lane_base + (uint32_t)(NTILES * 128 + j * 64);
-        hc.o_base = cgp * OW;
+        hc.o_base = (PAIR ? (int)crank * 32 : 0) + cgp * OW;
         hc.O = O; hc.A = A;
         hc.slice_bits = head_slice_bits<OW>(sc, hc.o_base);
         hc.n_constraints = sc.n_constraints;
         hc.scale_smem = scale_smem;
         hc.pen_smem = pen_smem;
-        hc.part = part_smem + ((j * Q + cgp) * nparts) * 128 + r;              // [nparts] stride 128
-        const AStoreTmem astore{t_a};
+        // partial minima: slice crank * Q + cgp of the buffer the scorer warp (PAIR: of CTA 0) reads
+        float* part_slot0 = part_smem + ((j * NSL + (int)crank * Q + cgp) * nparts) * 128 + r;   // [nparts] stride 128
+        hc.part = part_slot0 + (PAIR ? part_buf_floats : 0);                  // s_0 counts as step -1: buffer 1
+        typename std::conditional<PAIR, AStorePair, AStoreTmem>::type astore;
+        astore.t_a = t_a;
+        const uint32_t my_xbar = smem_u32(&bars[1 + NTILES]);                 // PAIR: [2] mbarriers, 8 bytes apart
+        const uint32_t peer_xbar = PAIR ? cluster_map_u32(my_xbar, crank ^ 1u) : 0u;
+        const bool keeps_score = !PAIR || crank == 0;                         // this CTA's scorer warp is the live one
+        const uint32_t part_remote0 = (PAIR && crank != 0) ? cluster_map_u32(smem_u32(part_slot0), 0u) : 0u;
+        if constexpr (PAIR) {
+          astore.peer_slot = cluster_map_u32(smem_u32(xch_smem + cgp * 128 + r), crank ^ 1u);
+          astore.buf_off = (uint32_t)(Q * 128 * sizeof(uint4));               // buffer 1
+          astore.peer_bar = peer_xbar + 8u;
+          if (crank != 0) {                                                   // CTA 1: partial minima go to CTA 0 (peer)
+            hc.part_remote = part_remote0 + (uint32_t)(part_buf_floats * sizeof(float));
+            hc.part_mbar = peer_xbar + 8u;
+          }
+        }
+        // PAIR: hand this warp's slices of step t to the peer (t = -1: s_0) and, when a next step follows,
+        // fetch the peer's half of x_{t+1} into the A operand
+        auto exchange = [&](int t, bool next_step) {
+          if constexpr (PAIR) {
+            const uint32_t b = (uint32_t)t & 1u;
+            if (next_step) {
+              mbar_wait(my_xbar + 8u * b, (uint32_t)((t + 1) >> 1) & 1u);     // all of the peer's step-t stores have landed
+              const uint4 v = xch_smem[(b * Q + cgp) * 128 + r];
+              const uint32_t pk[4] = {v.x, v.y, v.z, v.w};
+              tmem_st<4>(t_a + (uint32_t)((((int)crank ^ 1) * 32 + cgp * 8) >> 1), pk);
+            }
+          }
+        };
         const float* s0_ptr = prm.states + (prm.state_per_row ? id.r_global : (int64_t)id.s) * prm.state_stride;
 
 #ifdef SIMBA_TC_TIMELINE
@@ -379,7 +485,10 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
           named_bar_arrive_n(kBarA + j, tile_bar_threads);
         };
         auto wait_accumulator = [&]() {
-          named_bar_sync_n(kBarAcc + j, tile_bar_threads);     // released by the issuer warp's arrive
+          // released by the issuer warp's arrive. (Letting the sixteen epilogue warps sleep on the commit
+          // mbarrier themselves is slower even in the one-tile variant: commit -> accumulator seen 496
+          // cycles instead of 408 through the relay, measured.)
+          named_bar_sync_n(kBarAcc + j, tile_bar_threads);
           tc_fence_after();
         };
 
@@ -442,8 +551,9 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
         prefetch_actions(0);
         head_first_pass<OW>(hc, astore, s0_ptr, row_ok, act_pf);
         prefetch_actions(1);
+        exchange(-1, true);
         publish_a();                                        // layer-0 input of step 0
-        named_bar_arrive_n(kBarPart + j, tile_bar_threads);  // partial minima of s_0 published (scorer warp)
+        if (keeps_score) named_bar_arrive_n(kBarPart + j, tile_bar_threads);  // partial minima of s_0 published (scorer warp)
 
         PhiloxState ps{0u, 0u, 0u, 0u, 0u, 0u};             // a noise block in flight across two layers (latency variant)
         for (int t = 0; t < H; ++t) {
@@ -503,35 +613,48 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
 
           // ---- Gaussian heads + state update + next input + partial minima (one fused pass) --------
           wait_accumulator();
-          named_bar_sync_n(kBarFree + j, tile_bar_threads);  // the scorer warp is done with the previous partials
+          if (keeps_score) named_bar_sync_n(kBarFree + j, tile_bar_threads);  // the scorer warp is done with the previous partials
           TL(40);
+          if constexpr (PAIR) {
+            hc.part = part_slot0 + (t & 1) * part_buf_floats;
+            astore.buf_off = (uint32_t)((t & 1) * Q * 128 * sizeof(uint4));
+            astore.peer_bar = peer_xbar + 8u * ((uint32_t)t & 1u);
+            if (crank != 0) {
+              hc.part_remote = part_remote0 + (uint32_t)((t & 1) * part_buf_floats * sizeof(float));
+              hc.part_mbar = astore.peer_bar;
+            }
+          }
           if (prm.sampling_propagation) head_step_pass<OW, true>(hc, noise, astore, t + 1 < H);
           else head_step_pass<OW, false>(hc, noise, astore, t + 1 < H);
           TL(41);
+          exchange(t, t + 1 < H);
           if (t + 1 < H) publish_a();                       // next step's layer 0 goes out
-          named_bar_arrive_n(kBarPart + j, tile_bar_threads);  // partial minima of s_{t+1} published (scorer warp)
+          if (keeps_score) named_bar_arrive_n(kBarPart + j, tile_bar_threads);  // partial minima of s_{t+1} published (scorer warp)
           TL(42);
         }
       }
     }
   }
 
+  if (threadIdx.x == 0 && !any_valid && cta_member() >= 0) mbar_wait(bar_w, 0);   // never exit with a bulk copy into this CTA's memory pending
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                     // no CTA exits while its peer may still write into its shared memory
   if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-static size_t tc_smem_bytes(int L, int ntiles, int q, int nparts) {
+static size_t tc_smem_bytes(int L, int ntiles, int q, int nparts, bool pair = false) {
   size_t b = (size_t)kAtomBytes + (size_t)L * 2 * kAtomBytes;      // weights
   b += (size_t)(L + 1) * 4096 + 4096;                              // bias K-blocks + ones tile
   b += 128 * sizeof(float);                                        // scaler
   b += kHeadParts * 64 * sizeof(float);                            // slice penalty table
-  b += (size_t)ntiles * q * nparts * 128 * sizeof(float);          // partial minima exchange
+  b += (size_t)ntiles * q * nparts * 128 * sizeof(float) * (pair ? 4 : 1);   // partial minima exchange (pair: 2 x 2 q slices)
+  if (pair) b += (size_t)2 * q * 128 * sizeof(uint4);              // next-input slices from the peer CTA
   if (ntiles > 1)                                                  // parking area of the two-tile variant:
     b += (size_t)(64 / q / 8) * (ntiles * q * 128) * sizeof(uint4);      // bf16x2 noise of the current step
   b += (size_t)8 * ntiles * 128 * sizeof(uint32_t);                      // per-row running objective
-  b += (1 + ntiles) * sizeof(uint64_t) + 2 * sizeof(uint32_t) + ntiles * sizeof(TileInfo) + sizeof(uint64_t);
+  b += (3 + ntiles) * sizeof(uint64_t) + 2 * sizeof(uint32_t) + ntiles * sizeof(TileInfo) + sizeof(uint64_t);
   return b + 1024;                                                 // alignment slack
 }
 
@@ -549,34 +672,51 @@ bool rollout_tc_two_tiles_fit(int L, int n_constraints) {
   return tc_smem_bytes(L, 2, 2, 1 + n_constraints) + 1024 <= kMaxSmem;
 }
 
-template <int NTILES, int Q>
+// whether the two-CTA latency variant (doubled partial-minima buffers + the peer exchange) fits
+bool rollout_tc_pair_fits(int L, int n_constraints) {
+  return tc_smem_bytes(L, 1, 4, 1 + n_constraints, true) + 1024 <= kMaxSmem;
+}
+
+template <int NTILES, int Q, bool PAIR>
 static cudaError_t launch_variant(const RolloutParams& prm, int n_tiles, cudaStream_t stream) {
-  const size_t smem = tc_smem_bytes(prm.L, NTILES, Q, 1 + prm.scorer.n_constraints);
+  const size_t smem = tc_smem_bytes(prm.L, NTILES, Q, 1 + prm.scorer.n_constraints, PAIR);
   // set on every launch: the attribute is per device and per function, and launches happen only at
   // graph capture or in the non-graph entry points, never on the replayed hot path
   {
-    cudaError_t e = cudaFuncSetAttribute(rollout_tc_kernel<NTILES, Q>,
+    cudaError_t e = cudaFuncSetAttribute(rollout_tc_kernel<NTILES, Q, PAIR>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  const int grid = (n_tiles + NTILES - 1) / NTILES;
+  const int grid = ((n_tiles + NTILES - 1) / NTILES) * (PAIR ? 2 : 1);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NTILES * Q * 128 + 64 * NTILES);             // epilogue warps + an issuer and a scorer warp per tile
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (PAIR) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (prm.pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = prm.pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, rollout_tc_kernel<NTILES, Q>, prm);
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, rollout_tc_kernel<NTILES, Q, PAIR>, prm);
 }
 
 cudaError_t launch_rollout_tc(const RolloutParams& prm, int n_tiles, cudaStream_t stream) {
   if (n_tiles == 0) return cudaSuccess;
-  if (prm.tc_tiles_per_cta == 2) return launch_variant<2, 2>(prm, n_tiles, stream);
-  return launch_variant<1, 4>(prm, n_tiles, stream);
+  if (prm.tc_tiles_per_cta == 2) return launch_variant<2, 2, false>(prm, n_tiles, stream);
+  if (prm.tc_pair) return launch_variant<1, 4, true>(prm, n_tiles, stream);
+  return launch_variant<1, 4, false>(prm, n_tiles, stream);
 }
 
 }  // namespace simba

@@ -129,6 +129,9 @@ struct HeadCtx {
   const float* scale_smem;
   const float* pen_smem;
   float* part;           // this thread's slot of the partial-minima exchange: part p at part[p * 128]
+  // two-CTA variant of rollout_tc.cu, CTA 1: the slot lives in CTA 0 (shared::cluster address of part p = 0,
+  // 0 = the slot is local) and every store completes 4 bytes on that CTA's mbarrier
+  uint32_t part_remote = 0, part_mbar = 0;
 };
 
 // sqrt(softplus(x) + 1e-4) on the MUFU path (mlp_ensemble.py:30, :192): ln(1 + e^x) =
@@ -194,6 +197,13 @@ __device__ __forceinline__ void head_store_actions(const HeadCtx& c, const float
 }
 
 __device__ __forceinline__ void head_publish(const HeadCtx& c, float gmin, const float (&cmin)[SIMBA_MAX_CONSTRAINTS]) {
+  if (c.part_remote != 0u) {
+    st_async_b32(c.part_remote, __float_as_uint(gmin), c.part_mbar);
+#pragma unroll
+    for (int q = 0; q < SIMBA_MAX_CONSTRAINTS; ++q)
+      if (q < c.n_constraints) st_async_b32(c.part_remote + (uint32_t)((1 + q) * 128 * 4), __float_as_uint(cmin[q]), c.part_mbar);
+    return;
+  }
   c.part[0] = gmin;
 #pragma unroll
   for (int q = 0; q < SIMBA_MAX_CONSTRAINTS; ++q)

@@ -125,6 +125,44 @@ def test_tc_two_tiles_per_cta_matches_one_tile():
     assert np.array_equal(outs[0][:, :500], outs[1])
 
 
+@pytest.mark.parametrize("draws", ["external", "philox"])
+@pytest.mark.parametrize("cfg", ["tiny", "c1"])
+def test_tc_cta_pair_variant_is_bit_identical_to_single_cta(draws, cfg, monkeypatch):
+    """Plans with at most half as many tiles as SMs run a cluster of two CTAs per tile (head pass split
+    by output columns, slices exchanged through DSMEM). Every per-row output must be bit-identical to
+    the one-CTA kernel (SIMBA_B200_NO_PAIR=1): same per-element arithmetic, minima are order-free."""
+    from simba_b200 import _lib
+    lib = _lib.load()
+    c = helpers.workload(cfg)
+    rng = np.random.default_rng(3)
+    acts = rng.uniform(-1, 1, (c['N'], c['H'], c['A'])).astype(np.float32)
+    B = c['P'] * c['N']
+    eps = rng.standard_normal((c['H'], B, c['O'])).astype(np.float32) if draws == "external" else None
+    outs = []
+    for no_pair in (False, True):
+        if no_pair:
+            monkeypatch.setenv("SIMBA_B200_NO_PAIR", "1")
+        else:
+            monkeypatch.delenv("SIMBA_B200_NO_PAIR", raising=False)
+        pol = helpers.cuda_policy(c, 'penalty', precision='bf16')
+        pl = pol._ensure_planner()
+        ret = torch.zeros(B, dtype=torch.float32, device='cuda')
+        mask = torch.zeros(B, dtype=torch.int64, device='cuda')
+        csum = torch.zeros(B, dtype=torch.float32, device='cuda')
+        d_state, d_acts = dev(c['state'][None]), dev(acts[None].copy())
+        d_eps = dev(eps[None].copy()) if eps is not None else None
+        for it in (0, 3):                                                  # two iterations' counters
+            _lib.check(lib.simba_rollout_score(pl, P(d_state), P(d_acts), P(d_eps) if d_eps is not None else None,
+                                               21, it, None, P(ret), P(mask), P(csum), None))
+            torch.cuda.synchronize()
+            outs.append((ret.cpu().numpy().copy(), mask.cpu().numpy().copy(), csum.cpu().numpy().copy()))
+    for a, b in zip(outs[:2], outs[2:]):
+        assert np.all(np.isfinite(a[0]))
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    assert not np.array_equal(outs[0][0], outs[1][0]) or draws == "external"
+
+
 def test_tc_wide_batched_states_philox_and_early_exit():
     """The wide (units = 400) kernel in production mode: Philox draws on the device, several states
     per call (tiles that straddle states), reproducible, equal to per-state plans fed with the same
