@@ -586,6 +586,7 @@ struct simba_planner {
   int tile_rows = 0;
   int tiles_per_cta = 1;
   int tc_pair = 0;
+  int n_sms = 0;
 
   bool use_pdl = false;        // programmatic dependent launch between rollout and fused update kernels
   bool fused_update = false;   // one rank, N <= 1024: reduce+select+refit(+next sample | finalize) in one kernel
@@ -735,6 +736,7 @@ extern "C" int simba_planner_create(simba_model_t* model, const simba_planner_co
     // few tiles (a single plan): two SMs per tile, the head pass split between them (rollout_tc.cu, PAIR)
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+    p->n_sms = sms;
     p->tc_pair = cfg->precision == SIMBA_PREC_BF16_TC && mc.units <= 128 && p->tiles_per_cta == 1 &&
                  (int)p->tiles.size() * 2 <= sms && rollout_tc_pair_fits(mc.n_layers, cfg->scorer.n_constraints) &&
                  getenv("SIMBA_B200_NO_PAIR") == nullptr;
@@ -894,6 +896,7 @@ static int do_rollout_score(simba_planner_t* p, const float* states, const float
   prm.row_return = row_return; prm.row_costmask = row_costmask; prm.row_costsum = row_costsum;
   prm.tc_tiles_per_cta = p->tiles_per_cta;
   prm.tc_pair = p->tc_pair;
+  prm.n_sms = p->n_sms;
   prm.pdl = pdl ? 1 : 0;
 #ifdef SIMBA_TC_TIMELINE
   // debug builds only (tools/tc_timeline.py): a scratch buffer for the kernels' clock64 stamps

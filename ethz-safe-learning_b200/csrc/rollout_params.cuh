@@ -29,6 +29,7 @@ struct RolloutParams {
   const void* bias_k16;       // [E][L+1][4096 B] bias K-blocks (see simba_model_commit)
   const float* bias_tc;       // [E][L+1][128] fp32 (heads: mu bias at [0, O), var bias at [64, 64+O))
   int32_t tc_tiles_per_cta;   // 1 (latency: small populations) or 2 (MMA / epilogue ping-pong)
+  int32_t n_sms;              // SMs of the planner's device (grid of the persistent tcgen05 kernels)
   int32_t tc_pair;            // one-tile variant only: a cluster of two CTAs per tile splits the head pass
   int32_t pdl;                // launch with programmatic stream serialization (fused plan path)
   float tc_scale_a[64];       // bf16 path: x_scaled[k] = fma(x[k], a[k], b[k]); zero beyond O + A

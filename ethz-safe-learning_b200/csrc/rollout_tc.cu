@@ -157,7 +157,13 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
   const int O = g.O, A = g.A;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;            // CTA within the pair
-  const int cta_tile0 = (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x) * NTILES;
+  // Persistent CTAs: work item = NTILES consecutive tiles of one member; CTA c takes items c, c + n_ctas, ...
+  // (the grid is one CTA per SM when there are more items than SMs). A CTA's items mostly belong to the
+  // same member, so the 144 KB weight set is staged once per member change instead of once per item, and
+  // TMEM allocation, barrier setup, table fills and the CTA launch itself are paid once per SM.
+  const int n_items = (prm.n_tiles + NTILES - 1) / NTILES;
+  const int cta_item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_ctas = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;       // PAIR: one item per cluster (launch_variant)
   const bool l0_pad_bias = (O + A + 2 <= 64);     // layer-0 bias rides in the K padding (see pack in api.cu)
   constexpr int n_quarters = 4;                   // TMEM lane quarters (= warps per column group) of a tile
   constexpr int tile_bar_threads = Q * 128 + 32;  // a tile's epilogue warps + one partner warp (issuer / scorer)
@@ -183,16 +189,33 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + NTILES + 2);
   TileInfo* tinfo = reinterpret_cast<TileInfo*>(tmem_slot + 2);
   uint64_t* seed_sh = reinterpret_cast<uint64_t*>(tinfo + NTILES);
+  int32_t* w_state_sh = reinterpret_cast<int32_t*>(seed_sh + 1);     // [0] member whose weights are staged, [1] loads issued
 
   const uint32_t bar_w = smem_u32(&bars[0]);
 
   pdl_launch_dependents();
   // member whose weights this CTA stages (-1: no rows at all); fixed geometry, readable before the PDL wait
-  auto cta_member = [&]() {
+  auto item_member = [&](int item) {
     int wm = -1;
     for (int q = 0; q < NTILES; ++q)
-      if (cta_tile0 + q < prm.n_tiles && prm.tiles[cta_tile0 + q].count > 0) wm = prm.tiles[cta_tile0 + q].member;
+      if (item * NTILES + q < prm.n_tiles && prm.tiles[item * NTILES + q].count > 0) wm = prm.tiles[item * NTILES + q].member;
     return wm;
+  };
+  // one TMA bulk copy per layer, all onto bars[0] (thread 0 only; every MMA that read the previous set has completed)
+  auto stage_weights = [&](int wm) {
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(prm.w_bf16) + (size_t)wm * prm.w_bf16_member_bytes;
+    const uint32_t bk_bytes = (uint32_t)(L + 1) * 4096u;
+    mbar_expect_tx(bar_w, w_bytes + bk_bytes);
+    uint32_t off = 0;
+    for (int l = 0; l <= L; ++l) {
+      const uint32_t nb = (l == 0) ? kAtomBytes : 2 * kAtomBytes;
+      bulk_g2s(smem_u32(w_smem + off), wsrc + off, nb, bar_w);
+      off += nb;
+    }
+    bulk_g2s(smem_u32(biask_smem), reinterpret_cast<const uint8_t*>(prm.bias_k16) + (size_t)wm * bk_bytes,
+             bk_bytes, bar_w);
+    w_state_sh[0] = wm;
+    w_state_sh[1] += 1;
   };
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
@@ -206,32 +229,48 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
     }
     fence_barrier_init();
     // The member's weights do not depend on the previous kernel (the tile list is fixed geometry), so
-    // their TMA copies start before the programmatic-dependency wait and overlap the CEM update's tail:
-    // one bulk copy per layer, all onto bars[0]. A CTA whose tiles turn out inactive still drains them.
-    {
-      const int wm = cta_member();
-      if (wm >= 0) {
-        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(prm.w_bf16) + (size_t)wm * prm.w_bf16_member_bytes;
-        const uint32_t bk_bytes = (uint32_t)(L + 1) * 4096u;
-        mbar_expect_tx(bar_w, w_bytes + bk_bytes);
-        uint32_t off = 0;
-        for (int l = 0; l <= L; ++l) {
-          const uint32_t nb = (l == 0) ? kAtomBytes : 2 * kAtomBytes;
-          bulk_g2s(smem_u32(w_smem + off), wsrc + off, nb, bar_w);
-          off += nb;
-        }
-        bulk_g2s(smem_u32(biask_smem), reinterpret_cast<const uint8_t*>(prm.bias_k16) + (size_t)wm * bk_bytes,
-                 bk_bytes, bar_w);
-      }
-    }
+    // the copies for the first item start before the programmatic-dependency wait and overlap the CEM
+    // update's tail. A CTA whose tiles turn out inactive still drains them before it exits.
+    w_state_sh[0] = -1;
+    w_state_sh[1] = 0;
+    const int wm = cta_item0 < n_items ? item_member(cta_item0) : -1;
+    if (wm >= 0) stage_weights(wm);
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   // everything above is independent of the previous kernel (the CEM update that wrote the actions
   // and the active flags); from here on its results are needed
   pdl_wait_prior_grid();
   if (threadIdx.x == 0) *seed_sh = prm.seed_ptr ? *prm.seed_ptr : prm.seed;
+  if (warp < kEpiWarps) {
+    // constant tables of this CTA (all epilogue threads cooperate)
+    // A operand of the bias K-step: ones[m][0] = ones[m][1] = 1, rest 0 (same core-matrix layout)
+    for (int i = threadIdx.x; i < 1024; i += kEpiThreads) {
+      const int byte = i * 4;                           // [16 groups][2 K halves][8 rows][16 B]
+      const bool first = ((byte & 255) < 128) && ((byte & 15) == 0);   // K half 0, elements 0 and 1
+      reinterpret_cast<uint32_t*>(ones_smem)[i] = first ? 0x3F803F80u : 0u;
+    }
+    fence_proxy_async();                                // generic-proxy writes -> visible to the MMA
+    head_tables_init(scale_smem, pen_smem, prm.tc_scale_a, prm.tc_scale_b, prm.scorer,
+                     l0_pad_bias ? O + A : -1, threadIdx.x, kEpiThreads);
+  }
+  if (PAIR && threadIdx.x == 0) {
+    // arm the exchange barriers for s_0 (step -1, barrier 1) and step 0 (barrier 0); see the scorer warps
+    const uint32_t per_step = crank == 0 ? (uint32_t)(kEpiThreads * 4 * nparts) : 0u;
+    mbar_expect_tx(smem_u32(&bars[2 + NTILES]), per_step + (uint32_t)(kEpiThreads * 16));
+    const uint32_t b0 = per_step + (1 < H ? (uint32_t)(kEpiThreads * 16) : 0u);
+    if (b0 != 0u) mbar_expect_tx(smem_u32(&bars[1 + NTILES]), b0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (PAIR) cluster_sync_all();                                 // the peer's mbarriers are armed before any store can reach them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  uint32_t ph = 0;                                    // phase of the tile's commit mbarrier (issuer warps), runs across items
+
+#pragma unroll 1
+  for (int item = cta_item0; item < n_items; item += n_ctas) {
   if (threadIdx.x < NTILES) {
-    const int ti = cta_tile0 + threadIdx.x;
+    const int ti = item * NTILES + threadIdx.x;
     TileInfo info{0, 0, 0, 0};
     if (ti < prm.n_tiles) {
       const Tile t = prm.tiles[ti];
@@ -246,23 +285,19 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
     }
     tinfo[threadIdx.x] = info;
   }
-  if (PAIR && threadIdx.x == 0) {
-    // arm the exchange barriers for s_0 (step -1, barrier 1) and step 0 (barrier 0); see the scorer warps
-    const uint32_t per_step = crank == 0 ? (uint32_t)(kEpiThreads * 4 * nparts) : 0u;
-    mbar_expect_tx(smem_u32(&bars[2 + NTILES]), per_step + (uint32_t)(kEpiThreads * 16));
-    const uint32_t b0 = per_step + (1 < H ? (uint32_t)(kEpiThreads * 16) : 0u);
-    if (b0 != 0u) mbar_expect_tx(smem_u32(&bars[1 + NTILES]), b0);
-  }
-  tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();                                 // the peer's mbarriers are armed before any store can reach them
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
   bool any_valid = false;
+  int member = -1;
 #pragma unroll
   for (int j = 0; j < NTILES; ++j)
-    if (tinfo[j].valid) any_valid = true;
+    if (tinfo[j].valid) { any_valid = true; member = tinfo[j].member; }
+  // another member than the one staged: every MMA of the previous item has completed (its last accumulator
+  // was consumed before the CTA barrier that ended the item), so the set can be overwritten
+  if (threadIdx.x == 0 && any_valid && member != w_state_sh[0]) {
+    if (w_state_sh[1] > 0) mbar_wait(bar_w, (uint32_t)(w_state_sh[1] - 1) & 1u);   // a copy nobody waited for (inactive item)
+    stage_weights(member);
+  }
+  __syncthreads();
 
   if (any_valid) {
     if (warp >= kEpiWarps + NTILES) {
@@ -361,8 +396,7 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
         const uint32_t d_tmem = tmem_base + (uint32_t)j * 128;
         const uint32_t a_tmem = tmem_base + (uint32_t)(NTILES * 192 + j * 64);       // lane 0, A columns
         const uint64_t ones_desc = umma_desc_k16_noswizzle(smem_u32(ones_smem));
-        mbar_wait(bar_w, 0);                                  // weights have landed before the first MMA
-        uint32_t ph = 0;
+        mbar_wait(bar_w, (uint32_t)(w_state_sh[1] - 1) & 1u);   // this member's weights have landed before the first MMA
 #ifdef SIMBA_TC_TIMELINE
         const int tl_who = (j == 0 && lane == 0) ? 2 : -1;
 #endif
@@ -409,19 +443,6 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
       const int cgp = wl >> 2;                            // column group in [0, Q)
       const int r = (wl & 3) * 32 + lane;                 // row in tile == TMEM lane
       const TileInfo ti = tinfo[j];
-      // constant tables of this CTA (all epilogue threads cooperate)
-      {
-        // A operand of the bias K-step: ones[m][0] = ones[m][1] = 1, rest 0 (same core-matrix layout)
-        for (int i = threadIdx.x; i < 1024; i += kEpiThreads) {
-          const int byte = i * 4;                           // [16 groups][2 K halves][8 rows][16 B]
-          const bool first = ((byte & 255) < 128) && ((byte & 15) == 0);   // K half 0, elements 0 and 1
-          reinterpret_cast<uint32_t*>(ones_smem)[i] = first ? 0x3F803F80u : 0u;
-        }
-        fence_proxy_async();                                // generic-proxy writes -> visible to the MMA
-        head_tables_init(scale_smem, pen_smem, prm.tc_scale_a, prm.tc_scale_b, prm.scorer,
-                         l0_pad_bias ? O + A : -1, threadIdx.x, kEpiThreads);
-        named_bar_sync<kEpiThreads>(1);
-      }
       if (ti.valid) {
         const bool row_ok = r < ti.count;
         const RowId id = decode_row(g, ti.member, ti.k0 + (row_ok ? r : 0));
@@ -636,7 +657,12 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
     }
   }
 
-  if (threadIdx.x == 0 && !any_valid && cta_member() >= 0) mbar_wait(bar_w, 0);   // never exit with a bulk copy into this CTA's memory pending
+  tc_fence_before();
+  __syncthreads();                                  // end of the item: tile info, exchange buffers and TMEM columns are free again
+  tc_fence_after();
+  }  // items
+
+  if (threadIdx.x == 0 && w_state_sh[1] > 0) mbar_wait(bar_w, (uint32_t)(w_state_sh[1] - 1) & 1u);   // never exit with a bulk copy into this CTA's memory pending
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();                     // no CTA exits while its peer may still write into its shared memory
@@ -654,7 +680,7 @@ static size_t tc_smem_bytes(int L, int ntiles, int q, int nparts, bool pair = fa
   if (ntiles > 1)                                                  // parking area of the two-tile variant:
     b += (size_t)(64 / q / 8) * (ntiles * q * 128) * sizeof(uint4);      // bf16x2 noise of the current step
   b += (size_t)8 * ntiles * 128 * sizeof(uint32_t);                      // per-row running objective
-  b += (3 + ntiles) * sizeof(uint64_t) + 2 * sizeof(uint32_t) + ntiles * sizeof(TileInfo) + sizeof(uint64_t);
+  b += (3 + ntiles) * sizeof(uint64_t) + 2 * sizeof(uint32_t) + ntiles * sizeof(TileInfo) + sizeof(uint64_t) + 2 * sizeof(int32_t);
   return b + 1024;                                                 // alignment slack
 }
 
@@ -687,7 +713,11 @@ static cudaError_t launch_variant(const RolloutParams& prm, int n_tiles, cudaStr
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  const int grid = ((n_tiles + NTILES - 1) / NTILES) * (PAIR ? 2 : 1);
+  const int n_items = (n_tiles + NTILES - 1) / NTILES;
+  const int sms = prm.n_sms;
+  if (sms <= 0) return cudaErrorInvalidValue;
+  // persistent CTAs (one per SM, 1 CTA / SM by shared memory and TMEM); the pair variant runs one item per cluster
+  const int grid = PAIR ? 2 * n_items : (n_items < sms ? n_items : sms);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NTILES * Q * 128 + 64 * NTILES);             // epilogue warps + an issuer and a scorer warp per tile
