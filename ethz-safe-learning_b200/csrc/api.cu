@@ -1073,6 +1073,10 @@ static int enqueue_plan(simba_planner* p, cudaStream_t st, int* n_launches) {
       u.last = (it + 1 == c.iterations) ? 1 : 0;
       u.out_score = p->d_out_score;
       u.out_iters = p->d_out_iters;
+#ifdef SIMBA_TC_TIMELINE
+      if (const char* tlp = getenv("SIMBA_TC_TIMELINE_PTR"))
+        u.timeline = reinterpret_cast<long long*>(strtoull(tlp, nullptr, 10)) + (3 * 64 + 1 + it) * 64;
+#endif
       CUDA_TRY(launch_cem_update(u, st)); ++launches;
     }
     if (n_launches) *n_launches = launches;

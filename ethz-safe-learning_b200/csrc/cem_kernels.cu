@@ -16,35 +16,62 @@ namespace simba {
 // One thread = 4 consecutive flattened (h, a) elements of one candidate (= one Philox block).
 // =============================================================================================
 // one Philox block = 4 consecutive flattened (h, a) elements of candidate i of state s
-__device__ __forceinline__ void sample_values4(const SampleParams& p, int s, int i, int j, float (&out)[4]) {
+// n / d for 0 <= n < 2^22, 1 <= d < 2^22 with inv = 1.0f / d: a multiply and a fix-up instead of the
+// ~30-instruction integer division. The latency kernels below run 32 warps on one SM, where every
+// instruction all threads execute costs 8 issue cycles per scheduler.
+__device__ __forceinline__ int div_small(int n, int d, float inv) {
+  int q = (int)((float)n * inv);
+  const int r = n - q * d;
+  if (r < 0) --q;
+  else if (r >= d) ++q;
+  return q;
+}
+
+// the four N(0,1) draws of block j of candidate i: external (parity mode) or the ACTION stream
+__device__ __forceinline__ void sample_draws4(const SampleParams& p, uint64_t seed, int s, int i, int j, float (&z)[4]) {
   const int HA = p.H * p.A;
-  const long base = ((long)s * p.N + i) * HA + 4 * j;
-  float z[4];
   if (p.z != nullptr) {
+    const long base = ((long)s * p.N + i) * HA + 4 * j;
 #pragma unroll
     for (int q = 0; q < 4; ++q) z[q] = (4 * j + q < HA) ? p.z[base + q] : 0.0f;
   } else {
-    const float4 n = philox_normals<false>(p.seed_ptr ? *p.seed_ptr : p.seed, kStreamAction,
-                                           (uint32_t)s, (uint32_t)p.iteration, 0u, (uint32_t)i, (uint32_t)j);
+    const float4 n = philox_normals<false>(seed, kStreamAction, (uint32_t)s, (uint32_t)p.iteration, 0u, (uint32_t)i,
+                                           (uint32_t)j);
     z[0] = n.x; z[1] = n.y; z[2] = n.z; z[3] = n.w;
   }
+}
+// clip(z * sigma + mu) — cem_mpc.py:44-48. mu_s / sigma_s: this state's H * A values (global memory, or
+// the fused update kernel's shared copies)
+__device__ __forceinline__ void sample_apply4(const SampleParams& p, const float* mu_s, const float* sigma_s,
+                                              const float (&z)[4], int j, float (&out)[4]) {
+  const int HA = p.H * p.A;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int e = 4 * j + q;
     out[q] = 0.0f;
     if (e < HA) {
       const int a = e % p.A;
-      const float v = __fadd_rn(__fmul_rn(z[q], p.sigma[s * HA + e]), p.mu[s * HA + e]);
+      const float v = __fadd_rn(__fmul_rn(z[q], sigma_s[e]), mu_s[e]);
       out[q] = fminf(fmaxf(v, p.lb[a]), p.ub[a]);
     }
   }
 }
+__device__ __forceinline__ void sample_values4_from(const SampleParams& p, const float* mu_s, const float* sigma_s,
+                                                    uint64_t seed, int s, int i, int j, float (&out)[4]) {
+  float z[4];
+  sample_draws4(p, seed, s, i, j, z);
+  sample_apply4(p, mu_s, sigma_s, z, j, out);
+}
 
-__device__ __forceinline__ void sample_block_to(const SampleParams& p, int s, int i, int j, float* dst_all) {
+__device__ __forceinline__ void sample_values4(const SampleParams& p, int s, int i, int j, float (&out)[4]) {
+  const int HA = p.H * p.A;
+  sample_values4_from(p, p.mu + s * HA, p.sigma + s * HA, p.seed_ptr ? *p.seed_ptr : p.seed, s, i, j, out);
+}
+
+__device__ __forceinline__ void store_block4(const SampleParams& p, int s, int i, int j, const float (&out)[4],
+                                             float* dst_all) {
   const int HA = p.H * p.A;
   const long base = ((long)s * p.N + i) * HA + 4 * j;
-  float out[4];
-  sample_values4(p, s, i, j, out);
   if ((HA & 3) == 0) {
     *reinterpret_cast<float4*>(dst_all + base) = make_float4(out[0], out[1], out[2], out[3]);
   } else {
@@ -52,6 +79,12 @@ __device__ __forceinline__ void sample_block_to(const SampleParams& p, int s, in
     for (int q = 0; q < 4; ++q)
       if (4 * j + q < HA) dst_all[base + q] = out[q];
   }
+}
+
+__device__ __forceinline__ void sample_block_to(const SampleParams& p, int s, int i, int j, float* dst_all) {
+  float out[4];
+  sample_values4(p, s, i, j, out);
+  store_block4(p, s, i, j, out, dst_all);
 }
 
 __device__ __forceinline__ void sample_block(const SampleParams& p, int s, int i, int j) {
@@ -97,17 +130,20 @@ cudaError_t launch_sample_actions(const SampleParams& p, cudaStream_t st) {
 // the H x P popcount costs ~3 logic ops per particle and plane. Summation order over particles
 // is fixed (p ascending) => bit-identical on every rank.
 // =============================================================================================
-__device__ __forceinline__ float2 reduce_candidate(const ReduceParams& p, int s, int i) {
+// rows of candidate i: element base + q * stride of each array, q = 0 .. P - 1
+__device__ __forceinline__ float2 reduce_rows(const float* row_return, const uint64_t* row_costmask,
+                                              const float* row_costsum, long base, int stride, int P, int H,
+                                              int objective) {
   float ret = 0.0f, csum = 0.0f;
   uint64_t plane[8];
 #pragma unroll
   for (int b = 0; b < 8; ++b) plane[b] = 0ull;
 #pragma unroll 4
-  for (int q = 0; q < p.P; ++q) {
-    const long r = ((long)s * p.P + q) * p.N_local + i;
-    ret = __fadd_rn(ret, p.row_return[r]);
-    csum = __fadd_rn(csum, p.row_costsum[r]);
-    uint64_t carry = p.row_costmask[r];
+  for (int q = 0; q < P; ++q) {
+    const long r = base + (long)q * stride;
+    ret = __fadd_rn(ret, row_return[r]);
+    csum = __fadd_rn(csum, row_costsum[r]);
+    uint64_t carry = row_costmask[r];
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
       const uint64_t t = plane[b] & carry;
@@ -115,12 +151,12 @@ __device__ __forceinline__ float2 reduce_candidate(const ReduceParams& p, int s,
       carry = t;
     }
   }
-  const float mean_ret = __fdiv_rn(ret, (float)p.P);
+  const float mean_ret = __fdiv_rn(ret, (float)P);
   float cost = 0.0f;
-  if (p.objective == SIMBA_OBJ_LEAST_COST) {
-    cost = __fdiv_rn(csum, (float)p.P);
-  } else if (p.objective != SIMBA_OBJ_REWARD) {
-    uint64_t cand = (p.H >= 64) ? ~0ull : ((1ull << p.H) - 1ull);
+  if (objective == SIMBA_OBJ_LEAST_COST) {
+    cost = __fdiv_rn(csum, (float)P);
+  } else if (objective != SIMBA_OBJ_REWARD) {
+    uint64_t cand = (H >= 64) ? ~0ull : ((1ull << H) - 1ull);
     int maxc = 0;
 #pragma unroll
     for (int b = 7; b >= 0; --b) {
@@ -130,6 +166,11 @@ __device__ __forceinline__ float2 reduce_candidate(const ReduceParams& p, int s,
     cost = (float)maxc;
   }
   return make_float2(mean_ret, cost);
+}
+
+__device__ __forceinline__ float2 reduce_candidate(const ReduceParams& p, int s, int i) {
+  return reduce_rows(p.row_return, p.row_costmask, p.row_costsum, (long)s * p.P * p.N_local + i, p.N_local, p.P, p.H,
+                     p.objective);
 }
 
 __global__ void __launch_bounds__(256) score_reduce_kernel(ReduceParams p) {
@@ -607,16 +648,24 @@ cudaError_t launch_select_elites(const SelectParams& p, cudaStream_t st) {
 // =============================================================================================
 constexpr int kRefitThreads = 1024;
 
+#ifdef SIMBA_TC_TIMELINE
+__device__ long long* g_utl_ptr = nullptr;          // set by thread 0 of the fused update kernel (debug stamps)
+#define RTL(k) do { if (blockIdx.x == 0 && threadIdx.x == 0 && g_utl_ptr != nullptr) g_utl_ptr[k] = clock64(); } while (0)
+#else
+#define RTL(k) do { } while (0)
+#endif
 // `elite` may live in global or shared memory; `sh` needs (groups + 2) * HA floats.
 // Must be called by all kRefitThreads threads of the CTA.
-__device__ __forceinline__ void refit_body(const RefitParams& p, int s, const int* elite, float* sh) {
+__device__ __forceinline__ void refit_body(const RefitParams& p, int s, const int* elite, float* sh,
+                                           int* stopped_sh = nullptr, const float* acts_copy = nullptr) {
   const int HA = p.H * p.A;
-  const int groups = kRefitThreads / HA > 0 ? kRefitThreads / HA : 1;
+  const int groups = p.groups;                            // max(1, kRefitThreads / HA), from the launch function
   float* part = sh;
   float* mean = part + groups * HA;
   float* sig = mean + HA;
   const int tid = threadIdx.x;
-  const float* acts = p.actions + (long)s * p.N * HA;
+  // acts_copy: this state's [N, H * A] actions staged in shared memory by the fused update kernel
+  const float* acts = acts_copy != nullptr ? acts_copy : p.actions + (long)s * p.N * HA;
   const float kf = (float)p.K;
   if (p.regen) {
     // population sharding: elite rows that other ranks sampled are recomputed into the action buffer
@@ -629,55 +678,100 @@ __device__ __forceinline__ void refit_body(const RefitParams& p, int s, const in
     __syncthreads();
   }
 
-  const int c = tid % HA, grp = tid / HA;                  // HA <= 1024 (checked at creation)
+  // Loads that do not depend on the two passes are issued before them, so that their L2 round trips
+  // overlap the gathers (HA <= kRefitThreads, checked at creation: column cc == tid has one owner).
+  const bool owns_col = tid < HA;
+  float mu_old = 0.0f, sg_old = 0.0f;
+  int iters_old = 0;
+  if (owns_col) { mu_old = p.mu[s * HA + tid]; sg_old = p.sigma[s * HA + tid]; }
+  if (tid == 0 && p.iterations_run != nullptr) iters_old = p.iterations_run[s];
+
+  const int grp = div_small(tid, HA, 1.0f / (float)HA), c = tid - grp * HA;   // HA <= 1024 (checked at creation)
+  // Small elite sets (K <= 8 groups: the fused update of a single plan): a thread's at most eight gathered
+  // values stay in registers for the second pass. Same values, same accumulation order (k ascending).
+  RTL(10);
+  const bool small = p.K <= 8 * groups;
+  const int umax = small ? (p.K + groups - 1) / groups : 0;   // uniform: gathers per thread (1 for a single plan's K = 15)
+  const bool works = grp < groups && grp < p.K;               // this thread's group holds at least one elite
+  float held[8];
+  if (small && works) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (u < umax) {                                          // uniform branch: idle iterations are skipped, not predicated
+        const int k = grp + u * groups;
+        held[u] = 0.0f;
+        if (k < p.K) held[u] = acts_copy != nullptr ? acts_copy[elite[k] * HA + c] : acts[(long)elite[k] * HA + c];
+      }
+    }
+  }
   for (int pass = 0; pass < 2; ++pass) {
     if (grp < groups) {
       float acc = 0.0f;
-      const float m = pass ? mean[c] : 0.0f;
-      // gathers are independent: issue 8 at a time, accumulate in index order (deterministic)
-      int k = grp;
-      for (; k + 7 * groups < p.K; k += 8 * groups) {
-        float v[8];
+      if (small) {
+        if (works) {
+          const float m = pass ? mean[c] : 0.0f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = acts[(long)elite[k + u * groups] * HA + c];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (pass) { const float d = __fsub_rn(v[u], m); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
-          else acc = __fadd_rn(acc, v[u]);
+          for (int u = 0; u < 8; ++u) {
+            if (u < umax && grp + u * groups < p.K) {
+              if (pass) { const float d = __fsub_rn(held[u], m); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
+              else acc = __fadd_rn(acc, held[u]);
+            }
+          }
         }
-      }
-      for (; k < p.K; k += groups) {
-        const float v = acts[(long)elite[k] * HA + c];
-        if (pass) { const float d = __fsub_rn(v, m); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
-        else acc = __fadd_rn(acc, v);
+      } else {
+        const float m = pass ? mean[c] : 0.0f;
+        // gathers are independent: issue 8 at a time, accumulate in index order (deterministic)
+        int k = grp;
+        for (; k + 7 * groups < p.K; k += 8 * groups) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = acts[(long)elite[k + u * groups] * HA + c];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (pass) { const float d = __fsub_rn(v[u], m); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
+            else acc = __fadd_rn(acc, v[u]);
+          }
+        }
+        for (; k < p.K; k += groups) {
+          const float v = acts[(long)elite[k] * HA + c];
+          if (pass) { const float d = __fsub_rn(v, m); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
+          else acc = __fadd_rn(acc, v);
+        }
       }
       part[grp * HA + c] = acc;
     }
+    RTL(11 + 4 * pass);
     __syncthreads();
-    for (int cc = tid; cc < HA; cc += kRefitThreads) {
+    RTL(12 + 4 * pass);
+    if (owns_col) {
+      const int cc = tid;
       float tot = 0.0f;
-      for (int gI = 0; gI < groups; ++gI) tot = __fadd_rn(tot, part[gI * HA + cc]);
+#pragma unroll 8
+      for (int gI = 0; gI < groups; ++gI) tot = __fadd_rn(tot, part[gI * HA + cc]);   // fixed order; loads pipelined
       const float r = __fdiv_rn(tot, kf);
       if (pass == 0) mean[cc] = r;
       else {
         const float sd = sqrtf(r);                                        // cem_mpc.py:63
-        const float mu_new = __fadd_rn(__fmul_rn(p.smoothing, p.mu[s * HA + cc]),
-                                       __fmul_rn(p.one_minus_smoothing, mean[cc]));
-        const float sg_new = __fadd_rn(__fmul_rn(p.smoothing, p.sigma[s * HA + cc]),
-                                       __fmul_rn(p.one_minus_smoothing, sd));
+        const float mu_new = __fadd_rn(__fmul_rn(p.smoothing, mu_old), __fmul_rn(p.one_minus_smoothing, mean[cc]));
+        const float sg_new = __fadd_rn(__fmul_rn(p.smoothing, sg_old), __fmul_rn(p.one_minus_smoothing, sd));
         p.mu[s * HA + cc] = mu_new;                                       // cem_mpc.py:64-65
         p.sigma[s * HA + cc] = sg_new;
         sig[cc] = sg_new;
+        mean[cc] = mu_new;            // the fused update kernel samples the next iteration from these copies
       }
     }
+    RTL(13 + 4 * pass);
     __syncthreads();
+    RTL(14 + 4 * pass);
   }
   if (tid == 0) {
     float tot = 0.0f;
+#pragma unroll 8
     for (int cc = 0; cc < HA; ++cc) tot = __fadd_rn(tot, sig[cc]);
-    if (p.iterations_run != nullptr) p.iterations_run[s] += 1;
-    if (p.active != nullptr && __fdiv_rn(tot, (float)HA) <= p.stddev_threshold)  // cem_mpc.py:66-67
-      p.active[s] = 0;
+    if (p.iterations_run != nullptr) p.iterations_run[s] = iters_old + 1;
+    const bool stop = p.active != nullptr && __fdiv_rn(tot, (float)HA) <= p.stddev_threshold;  // cem_mpc.py:66-67
+    if (stop) p.active[s] = 0;
+    if (stopped_sh != nullptr) *stopped_sh = stop ? 1 : 0;
   }
 }
 
@@ -792,9 +886,11 @@ __global__ void __launch_bounds__(kRefitThreads) refit_cluster_kernel(RefitParam
   }
 }
 
-cudaError_t launch_refit(const RefitParams& p, cudaStream_t st) {
+cudaError_t launch_refit(const RefitParams& p_in, cudaStream_t st) {
+  RefitParams p = p_in;
   const int HA = p.H * p.A;
   const int groups = kRefitThreads / HA > 0 ? kRefitThreads / HA : 1;
+  p.groups = groups;
   if (p.K >= 2048) {
     if ((long)p.N * HA > 0x7fffffffL) return cudaErrorInvalidValue;   // 32-bit element offsets in the kernel
     const size_t smem = (size_t)(groups * HA + 3 * HA) * sizeof(float) +
@@ -841,43 +937,269 @@ cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t st) {
 // results); what it removes is 3-4 kernel boundaries per iteration on the latency-bound C1 plan.
 // Selection is rank-by-counting: thread i owns candidate i and counts the keys that beat it.
 // =============================================================================================
+#ifdef SIMBA_TC_TIMELINE
+#define UTL(k) do { if (u.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0) u.timeline[k] = clock64(); } while (0)
+#else
+#define UTL(k) do { } while (0)
+#endif
+// Particles gq, gq + G, ... of candidate i: per-step counts of set mask bits in byte lanes, W words of four
+// steps each (fully unrolled), added to the candidate's shared counters
+template <int W>
+__device__ __forceinline__ void count_steps(const unsigned long long* st_mask, uint32_t* cnt_sm, int i, int gq, int G,
+                                            int P, int N, int W4) {
+  uint32_t acc[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) acc[w] = 0u;
+  for (int q = gq; q < P; q += G) {
+    const unsigned long long m = st_mask[q * N + i];
+    const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+#pragma unroll
+    for (int w = 0; w < W; ++w)
+      acc[w] += ((((w < 8 ? lo : hi) >> (4 * (w & 7))) & 0xfu) * 0x00204081u) & 0x01010101u;
+  }
+#pragma unroll
+  for (int w = 0; w < W; ++w)
+    if (w < W4 && acc[w] != 0u) atomicAdd(&cnt_sm[i * W4 + w], acc[w]);
+}
+
+// Shared-memory staging of the fused update kernel (u.stage != 0), behind the elite list, 16-byte aligned:
+//   [rows] u64 cost masks, [rows] returns, [rows] cost sums   (rows = P * N: the rollout's per-row outputs)
+//   [N * HA] this state's current actions, [N * JB * 4] the next iteration's N(0,1) draws,
+//   [N] per-candidate maximum step count, [N] per-candidate rank
+__host__ __device__ inline size_t update_stage_bytes(int P, int N, int HA) {
+  const size_t rows = (size_t)P * N, JB = (size_t)(HA + 3) / 4;
+  return rows * 16 + (size_t)N * HA * 4 + (size_t)N * JB * 16 + (size_t)N * 8 + (size_t)(HA + 4) * 8 + (size_t)N * 64 + 96;
+}
+
 __global__ void __launch_bounds__(kRefitThreads) cem_update_kernel(UpdateParams u) {
-  // PDL: the next rollout may start its prologue (TMEM allocation, barrier init) now; this kernel
-  // needs the previous rollout's row outputs, so it waits for that grid first.
+  UTL(0);
+  // PDL: the next rollout may start its prologue (TMEM allocation, barrier init) now.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // The kernel is one dependent chain on a single SM (measured: 31 k cycles per iteration before this
+  // layout, a fifth of a C1 plan), so it is written for latency:
+  //   * it is resident long before the rollout it follows has finished, so everything that does not depend
+  //     on that rollout — the next iteration's N(0,1) draws: Philox + the accurate Box-Muller, 7 k cycles of
+  //     instruction issue on one SM — happens BEFORE the dependency wait, into shared memory;
+  //   * after the wait every global load is issued at once (one L2 round trip, ~2 k cycles here): the
+  //     rollout's per-row outputs and the state's current actions are staged in shared memory;
+  //   * the per-candidate work is spread over all 1024 threads (150 candidate threads were issue-latency
+  //     bound): per-step particle counts by (candidate, step), ranks by (candidate, key chunk), combined
+  //     with integer shared-memory atomics — exact, order-free;
+  //   * the refit gathers from the staged actions and the next actions are clip(z sigma + mu) from shared
+  //     copies. Floating-point arithmetic and its order are those of the separate kernels.
   const int s = blockIdx.x;
   const int tid = threadIdx.x;
-  extern __shared__ float sh[];                       // refit scratch, then keys / elite list
+  // refit scratch, then keys / elite list, then the staging area. All pointers are `sh + index` (no integer
+  // round trips), so the compiler keeps them in the shared address space: with generic pointers every
+  // staging store was a generic ST.E that serialised the global loads behind it (eight round trips).
+  extern __shared__ __align__(16) float sh[];
   const int HA = u.refit.H * u.refit.A;
-  const int groups = kRefitThreads / HA > 0 ? kRefitThreads / HA : 1;
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(sh + (groups + 2) * HA + ((groups + 2) * HA & 1));
-  int* elite_sh = reinterpret_cast<int*>(keys + u.select.N);
+  const int groups = u.refit.groups;
+  const int N = u.select.N, K = u.select.K;
+  const int P = u.reduce.P;
+  const int rows = P * N;
+  const int JB = (HA + 3) >> 2;
+  const int o_keys = (groups + 2) * HA + ((groups + 2) * HA & 1);       // float index, 8-byte aligned
+  const int o_elite = o_keys + 2 * N;
+  const int o_mask = (o_elite + K + 3) & ~3;                            // 16-byte aligned from here on
+  const int o_ret = o_mask + 2 * rows;
+  const int o_csum = o_ret + rows;
+  const int o_act = (o_csum + rows + 3) & ~3;
+  const int o_z = (o_act + N * HA + 3) & ~3;
+  const int o_maxc = o_z + N * JB * 4;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(sh + o_keys);
+  int* elite_sh = reinterpret_cast<int*>(sh + o_elite);
+  unsigned long long* st_mask = reinterpret_cast<unsigned long long*>(sh + o_mask);
+  float* st_ret = sh + o_ret;
+  float* st_csum = sh + o_csum;
+  float* act_sm = sh + o_act;
+  float* z_sm = sh + o_z;
+  int* maxc_sm = reinterpret_cast<int*>(sh + o_maxc);
+  int* rank_sm = maxc_sm + N;
+  const int o_lb = (o_maxc + 2 * N + 3) & ~3;
+  const int HA4 = (HA + 3) & ~3;
+  float* lb_sm = sh + o_lb;                                             // per-element action bounds [HA4] each
+  float* ub_sm = lb_sm + HA4;
+  const int W4 = (u.reduce.H + 3) >> 2;                                  // 32-bit words of four byte-wide step counters
+  uint32_t* cnt_sm = reinterpret_cast<uint32_t*>(ub_sm + HA4);           // [N][W4] particle counts per step
+  const float inv_JB = u.inv_JB, inv_N = u.inv_N;
   __shared__ int warp_sums[32];
   __shared__ int sh_total;
-  const int N = u.select.N, K = u.select.K;
+  __shared__ int sh_stopped;
+  const bool staged = u.stage != 0;
+  const bool presample = staged && !u.last && u.sample.z == nullptr;
+  // the plan's seed is uploaded before the plan's first kernel, which is a full dependency of everything here
+  const uint64_t seed_now = u.sample.seed_ptr ? *u.sample.seed_ptr : u.sample.seed;
+  if (presample) {
+    for (int idx = tid; idx < N * JB; idx += kRefitThreads) {
+      const int i = div_small(idx, JB, inv_JB);
+      float z[4];
+      sample_draws4(u.sample, seed_now, s, i, idx - i * JB, z);
+      *reinterpret_cast<float4*>(z_sm + 4 * idx) = make_float4(z[0], z[1], z[2], z[3]);
+    }
+  }
+  if (staged) {
+    for (int i = tid; i < 2 * N; i += kRefitThreads) maxc_sm[i] = 0;          // maxc_sm and rank_sm
+    for (int i = tid; i < N * W4; i += kRefitThreads) cnt_sm[i] = 0u;
+    for (int e = tid; e < HA4; e += kRefitThreads) {                          // bounds of element e (action dim e % A)
+      lb_sm[e] = e < HA ? u.sample.lb[e % u.sample.A] : 0.0f;
+      ub_sm[e] = e < HA ? u.sample.ub[e % u.sample.A] : 0.0f;
+    }
+  }
+  if (tid == 0) sh_stopped = 0;
+  UTL(7);
+  // this kernel needs the previous rollout's row outputs (and the update before it): wait for that grid
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  UTL(1);
+#ifdef SIMBA_TC_TIMELINE
+  if (blockIdx.x == 0 && threadIdx.x == 0) g_utl_ptr = u.timeline;
+#endif
+  // ---- every load whose address is known, unconditionally and at once --------------------------------
   const bool active = u.refit.active == nullptr || u.refit.active[s] != 0;
-  __syncthreads();                                    // everyone has read active[s] before refit clears it
+  const float best_prev = u.select.best_score[s];
+  if (staged) {
+    // batches of four elements per thread and array: all loads of a batch are in flight before the first store
+    const float* gret = u.reduce.row_return + (long)s * rows;
+    const uint64_t* gmask = u.reduce.row_costmask + (long)s * rows;
+    const float* gcsum = u.reduce.row_costsum + (long)s * rows;
+    const float* gact = u.select.actions + (long)s * N * HA;
+    const int n_act = N * HA;
+    if (((rows | n_act) & 3) == 0) {
+      // 16-byte loads: rows / 4 + rows / 4 + rows / 2 + n_act / 4 of them, a handful per thread, all in flight together
+      const int n1 = rows >> 2, n2 = rows >> 1, n3 = n_act >> 2;
+      const float4* g1 = reinterpret_cast<const float4*>(gret);
+      const float4* g2 = reinterpret_cast<const float4*>(gcsum);
+      const float4* g3 = reinterpret_cast<const float4*>(gmask);
+      const float4* g4 = reinterpret_cast<const float4*>(gact);
+      float4* d1 = reinterpret_cast<float4*>(st_ret);
+      float4* d2 = reinterpret_cast<float4*>(st_csum);
+      float4* d3 = reinterpret_cast<float4*>(st_mask);
+      float4* d4 = reinterpret_cast<float4*>(act_sm);
+      for (int b0 = 0; b0 < n2 || b0 < n3; b0 += 2 * kRefitThreads) {
+        float4 v1[2], v2[2], v3[2], v4[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int idx = b0 + q * kRefitThreads + tid;
+          if (idx < n1) { v1[q] = g1[idx]; v2[q] = g2[idx]; }
+          if (idx < n2) v3[q] = g3[idx];
+          if (idx < n3) v4[q] = g4[idx];
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int idx = b0 + q * kRefitThreads + tid;
+          if (idx < n1) { d1[idx] = v1[q]; d2[idx] = v2[q]; }
+          if (idx < n2) d3[idx] = v3[q];
+          if (idx < n3) d4[idx] = v4[q];
+        }
+      }
+    } else
+    for (int b0 = 0; b0 < rows || b0 < n_act; b0 += 4 * kRefitThreads) {
+      float r[4], c[4], av[4];
+      uint64_t m[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int idx = b0 + q * kRefitThreads + tid;
+        if (idx < rows) { r[q] = gret[idx]; m[q] = gmask[idx]; c[q] = gcsum[idx]; }
+        if (idx < n_act) av[q] = gact[idx];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int idx = b0 + q * kRefitThreads + tid;
+        if (idx < rows) { st_ret[idx] = r[q]; st_mask[idx] = m[q]; st_csum[idx] = c[q]; }
+        if (idx < n_act) act_sm[idx] = av[q];
+      }
+    }
+  }
+  __syncthreads();                                    // staged; everyone has read active[s] before refit clears it
+  UTL(8);
 
   if (active) {
     // ---- k8: (return, cost) of candidate tid --------------------------------------------------
     float2 pr = make_float2(0.0f, 0.0f);
     unsigned long long key = 0ull;
-    if (tid < N) {
+    const int objective = u.reduce.objective;
+    if (staged) {
+      const bool counts = objective != SIMBA_OBJ_LEAST_COST && objective != SIMBA_OBJ_REWARD && P < 256;
+      if (counts) {
+        // Number of particles whose done-masked cost bit is set, per step (safe_cem_mpc.py:110-120): every mask
+        // is read once. Thread (i, gq) takes particles gq, gq + G, ... of candidate i and spreads each nibble
+        // of the mask into four byte lanes (n * 0x00204081 & 0x01010101 puts bit k of n into byte k), so one
+        // 32-bit add counts four steps; the G partial words per candidate are combined with shared-memory
+        // atomics (bytes cannot overflow: P < 256). Integer arithmetic: exact and order-free.
+        const int G = u.chunks;
+        const int gq = div_small(tid, N, inv_N), i = tid - gq * N;
+        if (gq < G) {
+          if (W4 <= 4) count_steps<4>(st_mask, cnt_sm, i, gq, G, P, N, W4);        // H <= 16
+          else if (W4 <= 8) count_steps<8>(st_mask, cnt_sm, i, gq, G, P, N, W4);   // H <= 32
+          else count_steps<16>(st_mask, cnt_sm, i, gq, G, P, N, W4);
+        }
+      }
+      float ret = 0.0f, csum = 0.0f;
+      if (tid < N) {
+#pragma unroll 4
+        for (int q = 0; q < P; ++q) {                   // fixed order (p ascending), as reduce_rows
+          ret = __fadd_rn(ret, st_ret[q * N + tid]);
+          csum = __fadd_rn(csum, st_csum[q * N + tid]);
+        }
+      }
+      __syncthreads();
+      if (tid < N) {
+        float cost = 0.0f;
+        if (objective == SIMBA_OBJ_LEAST_COST) cost = __fdiv_rn(csum, (float)P);
+        else if (counts) {
+          uint32_t mx = 0u;                                   // max over the byte lanes (steps >= H are never set)
+          for (int w = 0; w < W4; ++w) {
+            const uint32_t c4 = cnt_sm[tid * W4 + w];
+            mx = max(max(mx, c4 & 0xffu), max((c4 >> 8) & 0xffu, max((c4 >> 16) & 0xffu, c4 >> 24)));
+          }
+          cost = (float)mx;
+        } else if (objective != SIMBA_OBJ_REWARD) {
+          cost = reduce_rows(st_ret, reinterpret_cast<const uint64_t*>(st_mask), st_csum, tid, N, P, u.reduce.H, objective).y;
+        }
+        pr = make_float2(__fdiv_rn(ret, (float)P), cost);
+      }
+    } else if (tid < N) {
       pr = reduce_candidate(u.reduce, s, tid);
+    }
+    if (tid < N) {
       if (u.reduce.out_pairs != nullptr) reinterpret_cast<float2*>(u.reduce.out_pairs)[(long)s * N + tid] = pr;
       key = pair_key(u.select.objective, pr.x, pr.y, u.select.c_max);
+      // Rank key: the order key with the index folded in (lower index wins ties), so that one 64-bit compare
+      // decides "j beats i": class bit 63 -> bit 50, bits 32..39 (violations, FEASIBLE_FIRST) -> 42..49, the
+      // ordered score -> bits 10..41, 1023 - index in the low ten bits (N <= 1024 on this path).
+      if (staged)
+        key = ((key >> 63) << 50) | (((key >> 32) & 0xffull) << 42) | ((key & 0xffffffffull) << 10) |
+              (unsigned long long)(1023 - tid);
       keys[tid] = key;
     }
+    UTL(9);
     __syncthreads();
+    UTL(2);
     // ---- k9: rank by counting (ties -> lower index), ordered compaction, best-so-far ------------
     int rank = 0;
-    if (tid < N)
+    const int chunks = u.chunks;                        // key chunks per candidate: kRefitThreads / N
+    if (staged && chunks > 1) {
+      const int ch = div_small(tid, N, inv_N), i = tid - ch * N;
+      if (ch < chunks) {
+        const int per = u.per;
+        const int j0 = ch * per, j1 = min(N, j0 + per);
+        const unsigned long long ki = keys[i];
+        int cnt = 0;
+#pragma unroll 5
+        for (int jn = j0; jn < j1; ++jn) cnt += keys[jn] > ki ? 1 : 0;      // rank keys are unique
+        if (cnt > 0) atomicAdd(&rank_sm[i], cnt);
+      }
+      __syncthreads();
+      if (tid < N) rank = rank_sm[tid];
+    } else if (tid < N) {
+#pragma unroll 8
       for (int jn = 0; jn < N; ++jn) {
         const unsigned long long kj = keys[jn];
-        rank += (kj > key || (kj == key && jn < tid)) ? 1 : 0;
+        rank += (kj > key || (kj == key && jn < tid)) ? 1 : 0;   // also right for rank keys (never equal)
       }
+    }
     const int sel = (tid < N && rank < K) ? 1 : 0;
+    UTL(3);
     const int pos = block_exclusive_scan<kRefitThreads>(sel, warp_sums, &sh_total);
     if (sel) {
       elite_sh[pos] = tid;
@@ -887,23 +1209,54 @@ __global__ void __launch_bounds__(kRefitThreads) cem_update_kernel(UpdateParams 
       u.select.out_scores[(long)s * N + tid] = pair_score(u.select.objective, pr.x, pr.y, u.select.c_max);
     if (tid < N && rank == 0) {                                   // argmax, first max
       const float top_score = pair_score(u.select.objective, pr.x, pr.y, u.select.c_max);
-      if (top_score > u.select.best_score[s]) {                   // cem_mpc.py:58 strict '>'
-        for (int a = 0; a < u.select.A; ++a)
-          u.select.best_action[s * u.select.A + a] = u.select.actions[((long)s * N + tid) * HA + a];
+      if (top_score > best_prev) {                                // cem_mpc.py:58 strict '>'
+        const float* arow = staged ? act_sm + tid * HA : u.select.actions + ((long)s * N + tid) * HA;
+        for (int a = 0; a < u.select.A; ++a) u.select.best_action[s * u.select.A + a] = arow[a];
         u.select.best_score[s] = top_score;
       }
     }
     __syncthreads();
+    UTL(4);
     // ---- k10: refit (also clears active[s] when the stddev threshold is met) --------------------
-    refit_body(u.refit, s, elite_sh, sh);
+    refit_body(u.refit, s, elite_sh, sh, &sh_stopped, staged ? act_sm : nullptr);
     __syncthreads();
+    UTL(5);
   }
   if (!u.last) {
     // ---- k1 of the next iteration (skipped for states that just stopped, like the early break) --
-    const bool still = u.refit.active == nullptr || u.refit.active[s] != 0;
-    if (active && still) {
-      const int JB = (HA + 3) >> 2;
-      for (int idx = tid; idx < N * JB; idx += kRefitThreads) sample_block(u.sample, s, idx / JB, idx % JB);
+    if (active && sh_stopped == 0) {
+      const float* mu_s = sh + groups * HA;            // refit_body left mu_new / sigma_new of this state here
+      const float* sigma_s = sh + (groups + 1) * HA;
+      for (int idx = tid; idx < N * JB; idx += kRefitThreads) {
+        const int i = div_small(idx, JB, inv_JB), j = idx - i * JB;
+        float z[4], out[4];
+        if (presample) {
+          const float4 zz = *reinterpret_cast<const float4*>(z_sm + 4 * idx);
+          z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
+        } else {
+          sample_draws4(u.sample, seed_now, s, i, j, z);
+        }
+        if (staged && (HA & 3) == 0) {
+          // sample_apply4 on 16-byte shared-memory reads: mu, sigma and the per-element bounds of elements 4 j .. 4 j + 3
+          const float4 m4 = *reinterpret_cast<const float4*>(mu_s + 4 * j), s4 = *reinterpret_cast<const float4*>(sigma_s + 4 * j);
+          const float4 l4 = *reinterpret_cast<const float4*>(lb_sm + 4 * j), u4 = *reinterpret_cast<const float4*>(ub_sm + 4 * j);
+          out[0] = fminf(fmaxf(__fadd_rn(__fmul_rn(z[0], s4.x), m4.x), l4.x), u4.x);
+          out[1] = fminf(fmaxf(__fadd_rn(__fmul_rn(z[1], s4.y), m4.y), l4.y), u4.y);
+          out[2] = fminf(fmaxf(__fadd_rn(__fmul_rn(z[2], s4.z), m4.z), l4.z), u4.z);
+          out[3] = fminf(fmaxf(__fadd_rn(__fmul_rn(z[3], s4.w), m4.w), l4.w), u4.w);
+        } else if (staged) {
+          // sample_apply4 with the per-element bounds from shared memory (no e % A, no indexed constant loads)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int e = 4 * j + q;                    // < HA4: the tables are padded
+            const float v = __fadd_rn(__fmul_rn(z[q], sigma_s[e < HA ? e : 0]), mu_s[e < HA ? e : 0]);
+            out[q] = e < HA ? fminf(fmaxf(v, lb_sm[e]), ub_sm[e]) : 0.0f;
+          }
+        } else {
+          sample_apply4(u.sample, mu_s, sigma_s, z, j, out);
+        }
+        store_block4(u.sample, s, i, j, out, u.sample.out);
+      }
     }
   } else {
     // ---- k11 + plan outputs ----------------------------------------------------------------------
@@ -915,13 +1268,28 @@ __global__ void __launch_bounds__(kRefitThreads) cem_update_kernel(UpdateParams 
       if (u.out_iters != nullptr) u.out_iters[s] = u.refit.iterations_run[s];
     }
   }
+  UTL(6);
 }
 
-cudaError_t launch_cem_update(const UpdateParams& u, cudaStream_t st) {
+cudaError_t launch_cem_update(const UpdateParams& u_in, cudaStream_t st) {
+  UpdateParams u = u_in;
   const int HA = u.refit.H * u.refit.A;
   const int groups = kRefitThreads / HA > 0 ? kRefitThreads / HA : 1;
+  u.refit.groups = groups;
+  u.chunks = kRefitThreads / u.select.N > 0 ? kRefitThreads / u.select.N : 1;
+  u.per = (u.select.N + u.chunks - 1) / u.chunks;
+  u.inv_N = 1.0f / (float)u.select.N;
+  u.inv_JB = 1.0f / (float)((HA + 3) / 4);
   size_t smem = (size_t)((groups + 2) * HA + 1) * sizeof(float);
   smem = (smem + 7) / 8 * 8 + (size_t)u.select.N * 8 + (size_t)u.select.K * 4 + 16;
+  // the staging area (rows, actions, draws; see update_stage_bytes), when it fits
+  const size_t stage = update_stage_bytes(u.reduce.P, u.select.N, HA);
+  u.stage = (smem + stage + 1024 <= 200 * 1024 && u.select.N <= kRefitThreads) ? 1 : 0;
+  if (u.stage) smem += stage;
+  {
+    cudaError_t e = cudaFuncSetAttribute(cem_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(u.refit.S);
   cfg.blockDim = dim3(kRefitThreads);

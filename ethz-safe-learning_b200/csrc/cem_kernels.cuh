@@ -54,6 +54,7 @@ struct RefitParams {                  // cem_mpc.py:61-67
   float* sigma;
   int32_t* active;
   int32_t* iterations_run;
+  int32_t groups;                     // set by the launch functions: max(1, threads / (H * A)) row groups of the gather
   int32_t regen;                      // elite rows sampled by other ranks are recomputed into `actions` first
   SampleParams sample;                // (same counters => bit-identical to the owner rank's rows)
 };
@@ -87,8 +88,12 @@ struct UpdateParams {                 // fused k8 + k9 + k10 (+ next k1 | k11): 
   FinalizeParams finalize;            // used when last
   int32_t last;
   int32_t pdl;                        // launch with programmatic stream serialization
+  int32_t stage;                      // set by launch_cem_update: rows, actions and draws of a state fit in shared memory
+  int32_t chunks, per;                // set by launch_cem_update: threads / N key chunks per candidate, keys per chunk
+  float inv_N, inv_JB;                // set by launch_cem_update: reciprocals for div_small
   float* out_score;
   int32_t* out_iters;
+  long long* timeline;                // -DSIMBA_TC_TIMELINE builds: clock64 stamps of the phases (tools/tc_timeline.py)
 };
 
 cudaError_t launch_cem_update(const UpdateParams& u, cudaStream_t st);

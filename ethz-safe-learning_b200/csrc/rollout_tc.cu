@@ -193,6 +193,14 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
 
   const uint32_t bar_w = smem_u32(&bars[0]);
 
+#ifdef SIMBA_TC_TIMELINE
+  // launch anatomy (thread 0 of CTA 0): row 3 of the timeline = entry, setup done, PDL wait passed, first
+  // A published, items done, exit
+#define TLK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) prm.timeline[(3 * 64) * 64 + (k)] = clock64(); } while (0)
+#else
+#define TLK(k) do { } while (0)
+#endif
+  TLK(0);
   pdl_launch_dependents();
   // member whose weights this CTA stages (-1: no rows at all); fixed geometry, readable before the PDL wait
   auto item_member = [&](int item) {
@@ -236,11 +244,17 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
     const int wm = cta_item0 < n_items ? item_member(cta_item0) : -1;
     if (wm >= 0) stage_weights(wm);
   }
+  auto load_tile = [&](int ti) {                                // fixed geometry: valid = has rows
+    TileInfo info{0, 0, 0, 0};
+    if (ti < prm.n_tiles) {
+      const Tile t = prm.tiles[ti];
+      info.member = t.member; info.k0 = t.k0; info.count = t.count;
+      info.valid = t.count > 0 ? 1 : 0;
+    }
+    return info;
+  };
+  if (threadIdx.x < NTILES) tinfo[threadIdx.x] = load_tile(cta_item0 * NTILES + threadIdx.x);
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
-  // everything above is independent of the previous kernel (the CEM update that wrote the actions
-  // and the active flags); from here on its results are needed
-  pdl_wait_prior_grid();
-  if (threadIdx.x == 0) *seed_sh = prm.seed_ptr ? *prm.seed_ptr : prm.seed;
   if (warp < kEpiWarps) {
     // constant tables of this CTA (all epilogue threads cooperate)
     // A operand of the bias K-step: ones[m][0] = ones[m][1] = 1, rest 0 (same core-matrix layout)
@@ -265,22 +279,24 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
   if (PAIR) cluster_sync_all();                                 // the peer's mbarriers are armed before any store can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  TLK(1);
+  // everything above (barriers, the first weight copy, TMEM, constant tables, the cluster handshake) is
+  // independent of the previous kernel — the CEM update that wrote the actions, the active flags and the
+  // seed — and overlaps its tail under programmatic dependent launch; from here on its results are needed
+  pdl_wait_prior_grid();
+  TLK(2);
+  if (threadIdx.x == 0) *seed_sh = prm.seed_ptr ? *prm.seed_ptr : prm.seed;   // published by the item loop's first barrier
   uint32_t ph = 0;                                    // phase of the tile's commit mbarrier (issuer warps), runs across items
 
 #pragma unroll 1
   for (int item = cta_item0; item < n_items; item += n_ctas) {
   if (threadIdx.x < NTILES) {
-    const int ti = item * NTILES + threadIdx.x;
-    TileInfo info{0, 0, 0, 0};
-    if (ti < prm.n_tiles) {
-      const Tile t = prm.tiles[ti];
-      info.member = t.member; info.k0 = t.k0; info.count = t.count;
-      bool any = t.count > 0;
-      if (any && prm.active != nullptr) {                     // cem_mpc.py:66-67 early exit
-        const int m = g.rows_per_state[t.member];
-        any = false;
-        for (int s = t.k0 / m; s <= (t.k0 + t.count - 1) / m; ++s) any = any || prm.active[s] != 0;
-      }
+    TileInfo info = tinfo[threadIdx.x];                       // first item: fetched before the PDL wait
+    if (item != cta_item0) info = load_tile(item * NTILES + threadIdx.x);
+    if (info.valid && prm.active != nullptr) {                // cem_mpc.py:66-67 early exit
+      const int m = g.rows_per_state[info.member];
+      bool any = false;
+      for (int s = info.k0 / m; s <= (info.k0 + info.count - 1) / m; ++s) any = any || prm.active[s] != 0;
       info.valid = any ? 1 : 0;
     }
     tinfo[threadIdx.x] = info;
@@ -574,6 +590,7 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
         prefetch_actions(1);
         exchange(-1, true);
         publish_a();                                        // layer-0 input of step 0
+        TLK(3);
         if (keeps_score) named_bar_arrive_n(kBarPart + j, tile_bar_threads);  // partial minima of s_0 published (scorer warp)
 
         PhiloxState ps{0u, 0u, 0u, 0u, 0u, 0u};             // a noise block in flight across two layers (latency variant)
@@ -665,8 +682,13 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
   if (threadIdx.x == 0 && w_state_sh[1] > 0) mbar_wait(bar_w, (uint32_t)(w_state_sh[1] - 1) & 1u);   // never exit with a bulk copy into this CTA's memory pending
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();                     // no CTA exits while its peer may still write into its shared memory
+  // PAIR: no cluster barrier is needed here. The last stores into the peer's memory are the step H - 2 input
+  // slices, which the peer consumed before its last step, and CTA 1's last partial minima, which CTA 0's
+  // scorer warp waited for before the barrier above; st.async data travels from registers, so the sender
+  // may exit first.
+  TLK(4);
   if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+  TLK(5);
 }
 
 // ---- host side ------------------------------------------------------------------------------------

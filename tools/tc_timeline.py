@@ -23,7 +23,7 @@ acts = torch.empty((S, N, H, A), device='cuda').uniform_(-1, 1)
 ret = torch.empty((S, P_, N), device='cuda'); msk = torch.empty((S, P_, N), dtype=torch.int64, device='cuda')
 csum = torch.empty((S, P_, N), device='cuda')
 # the timeline build stamps into prm.timeline, handed in through the env hook of the debug build
-tl = torch.zeros((3, 64, 64), dtype=torch.int64, device='cuda')
+tl = torch.zeros((4, 64, 64), dtype=torch.int64, device='cuda')
 os.environ['SIMBA_TC_TIMELINE_PTR'] = str(tl.data_ptr())
 p = lambda t: C.c_void_p(t.data_ptr())
 for it in range(3):
@@ -63,6 +63,9 @@ print("== noise block detail, epilogue warp 0 (last block of the step): philox r
 for step in range(2, min(H - 1, 8)):
     ev = t[0, step]
     print("step %2d philox %5d  box-muller %5d" % (step, ev[51] - ev[50], ev[52] - ev[51]))
+k = t[3, 0]
+print("== launch anatomy, thread 0 of CTA 0 (cycles since kernel entry): setup done %d, PDL wait passed %d, first A published %d, "
+      "all items done %d, exit %d" % tuple(int(k[i] - k[0]) for i in range(1, 6)))
 print("== issuer warp of tile 0 (cycles since epilogue warp 0's step start; layer: A-ready seen -> committed)")
 for step in range(2, min(H - 1, 8)):
     base = t[0, step][0]

@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Phase stamps of the fused CEM update kernel inside whole C1 plans (needs the -DSIMBA_TC_TIMELINE build:
+SIMBA_B200_LIB=.../libsimba_b200_tl.so python tools/update_timeline.py)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'ethz-safe-learning_b200')]
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from simba_b200 import synthetic  # noqa: E402
+
+c = synthetic.make_workload('c1')
+tl = torch.zeros((4, 64, 64), dtype=torch.int64, device='cuda')
+os.environ['SIMBA_TC_TIMELINE_PTR'] = str(tl.data_ptr())
+pol = synthetic.build_policy(c, 'penalty', precision='bf16', seed=1)
+for rep in range(3):
+    pol.do_generate_action(c['state'], seed=5 + rep)
+torch.cuda.synchronize()
+t = tl.cpu().numpy()
+names = ['entry', 'PDL wait passed', 'scores + keys', 'ranked', 'elites + best', 'refit', 'sampled / finalised']
+for it in range(c['I']):
+    ev = t[3, 1 + it]
+    print("iteration %d: " % it + ', '.join("%s %d" % (names[k], ev[k] - ev[1]) for k in range(2, 7)))
+    print("   detail (cycles after the wait): loads issued %d, staged %d, scores done (thread 0) %d | refit: start %d, "
+          % tuple(ev[k] - ev[1] for k in (7, 8, 9, 10))
+          + ', '.join("pass%d part %d sync %d totals %d sync %d" % ((ps,) + tuple(ev[11 + 4 * ps + q] - ev[1] for q in range(4)))
+                      for ps in range(2)))
