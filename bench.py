@@ -323,7 +323,7 @@ def main():
     peak_tf = peaks.get('bf16_tflops', 1590.0)
     achieved_tf = flops_per_launch / (roll_ms * 1e-3) / 1e12
     ms_plan = ms.mean()
-    kernel_name = "rollout_tc_kernel<1,4>" if precision == 'bf16' else "rollout_f32_kernel"
+    kernel_name = "rollout_tc_kernel<1,4,pair>" if precision == 'bf16' else "rollout_f32_kernel"
     roofline = {"kernel": kernel_name,
                 "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the CURRENT kernel at this shape,
@@ -333,8 +333,10 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PFLOP/s",
                 "flops_per_launch": flops_per_launch, "launch_ms": roll_ms,
                 "share_of_plan": c['I'] * roll_ms / ms_plan,
-                "note": "C1 is latency-bound: %d row tiles on 148 SMs, %d dependent GEMM stages per launch"
-                        % ((B + 127) // 128 if precision == 'bf16' else (B + 31) // 32, c['H'] * (c['L'] + 1))}
+                "note": "C1 is latency-bound: %d row tiles (%s) on 148 SMs, %d dependent GEMM stages per launch"
+                        % (c['E'] * ((B // c['E'] + 127) // 128) if precision == 'bf16' else (B + 31) // 32,
+                           "a cluster of two CTAs each" if precision == 'bf16' else "one CTA each",
+                           c['H'] * (c['L'] + 1))}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": float(ms_plan), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

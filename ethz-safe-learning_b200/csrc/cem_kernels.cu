@@ -938,7 +938,8 @@ cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t st) {
 // Selection is rank-by-counting: thread i owns candidate i and counts the keys that beat it.
 // =============================================================================================
 #ifdef SIMBA_TC_TIMELINE
-#define UTL(k) do { if (u.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0) u.timeline[k] = clock64(); } while (0)
+#define UTL(k) do { if (u.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { u.timeline[k] = clock64(); \
+    unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); u.timeline[32 + (k)] = (long long)gt_; } } while (0)
 #else
 #define UTL(k) do { } while (0)
 #endif

@@ -196,7 +196,9 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
 #ifdef SIMBA_TC_TIMELINE
   // launch anatomy (thread 0 of CTA 0): row 3 of the timeline = entry, setup done, PDL wait passed, first
   // A published, items done, exit
-#define TLK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) prm.timeline[(3 * 64) * 64 + (k)] = clock64(); } while (0)
+#define TLK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { prm.timeline[(3 * 64) * 64 + (k)] = clock64(); \
+    unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); \
+    prm.timeline[(3 * 64 + 10 + prm.iteration) * 64 + (k)] = (long long)gt_; } } while (0)
 #else
 #define TLK(k) do { } while (0)
 #endif

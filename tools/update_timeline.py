@@ -26,3 +26,11 @@ for it in range(c['I']):
           % tuple(ev[k] - ev[1] for k in (7, 8, 9, 10))
           + ', '.join("pass%d part %d sync %d totals %d sync %d" % ((ps,) + tuple(ev[11 + 4 * ps + q] - ev[1] for q in range(4)))
                       for ps in range(2)))
+
+print("== plan anatomy, ns on the global timer (rollout: thread 0 of CTA 0; update: thread 0)")
+for it in range(c['I']):
+    r = t[3, 10 + it]          # rollout: 0 entry, 1 setup done, 2 wait passed, 3 first A, 4 items done, 5 exit
+    uu = t[3, 1 + it][32:]     # update: 0 entry, 1 wait passed, 6 end
+    base = t[3, 10][2]
+    print("iteration %d: rollout wait passed %7d, first A %7d, items done %7d, exit %7d | update wait passed %7d, end %7d"
+          % (it, r[2] - base, r[3] - base, r[4] - base, r[5] - base, uu[1] - base, uu[6] - base))
