@@ -126,14 +126,16 @@ def test_tc_two_tiles_per_cta_matches_one_tile():
 
 
 @pytest.mark.parametrize("draws", ["external", "philox"])
-@pytest.mark.parametrize("cfg", ["tiny", "c1"])
+@pytest.mark.parametrize("cfg", ["tiny", "c1", "h1", "h2", "odd"])
 def test_tc_cta_pair_variant_is_bit_identical_to_single_cta(draws, cfg, monkeypatch):
     """Plans with at most half as many tiles as SMs run a cluster of two CTAs per tile (head pass split
     by output columns, slices exchanged through DSMEM). Every per-row output must be bit-identical to
     the one-CTA kernel (SIMBA_B200_NO_PAIR=1): same per-element arithmetic, minima are order-free."""
     from simba_b200 import _lib
     lib = _lib.load()
-    c = helpers.workload(cfg)
+    # h1 / h2: horizons with no / one exchange of next-step inputs; odd: ragged last tile, three members
+    over = {'h1': dict(H=1), 'h2': dict(H=2), 'odd': dict(E=3, N=37, P=9, H=5)}.get(cfg, {})
+    c = helpers.workload(cfg if not over else 'tiny', **over)
     rng = np.random.default_rng(3)
     acts = rng.uniform(-1, 1, (c['N'], c['H'], c['A'])).astype(np.float32)
     B = c['P'] * c['N']
