@@ -285,9 +285,27 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
   // everything above (barriers, the first weight copy, TMEM, constant tables, the cluster handshake) is
   // independent of the previous kernel — the CEM update that wrote the actions, the active flags and the
   // seed — and overlaps its tail under programmatic dependent launch; from here on its results are needed
-  pdl_wait_prior_grid();
+  // PAIR (one item per CTA, the latency path): the wait moves further down, into each warp role behind its
+  // own per-item setup (row decoding, pointers, the s_0 loads), which depends only on fixed geometry and on
+  // the states; each role then checks the active flags itself (late_gate).
+  constexpr bool kLateWait = PAIR;
+  if (!kLateWait) pdl_wait_prior_grid();
   TLK(2);
+  // (the plan's seed is uploaded before the plan's first kernel, a full dependency of every kernel of the plan)
   if (threadIdx.x == 0) *seed_sh = prm.seed_ptr ? *prm.seed_ptr : prm.seed;   // published by the item loop's first barrier
+  // whether any state a tile touches is still planning (cem_mpc.py:66-67 early exit)
+  auto tile_active = [&](const TileInfo& t) {
+    if (prm.active == nullptr) return true;
+    const int m = g.rows_per_state[t.member];
+    bool any = false;
+    for (int s = t.k0 / m; s <= (t.k0 + t.count - 1) / m; ++s) any = any || prm.active[s] != 0;
+    return any;
+  };
+  auto late_gate = [&](const TileInfo& t) {
+    if (!kLateWait) return true;                       // the item loop already waited and filtered
+    pdl_wait_prior_grid();
+    return tile_active(t);
+  };
   uint32_t ph = 0;                                    // phase of the tile's commit mbarrier (issuer warps), runs across items
 
 #pragma unroll 1
@@ -295,12 +313,7 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
   if (threadIdx.x < NTILES) {
     TileInfo info = tinfo[threadIdx.x];                       // first item: fetched before the PDL wait
     if (item != cta_item0) info = load_tile(item * NTILES + threadIdx.x);
-    if (info.valid && prm.active != nullptr) {                // cem_mpc.py:66-67 early exit
-      const int m = g.rows_per_state[info.member];
-      bool any = false;
-      for (int s = info.k0 / m; s <= (info.k0 + info.count - 1) / m; ++s) any = any || prm.active[s] != 0;
-      info.valid = any ? 1 : 0;
-    }
+    if (!kLateWait && info.valid) info.valid = tile_active(info) ? 1 : 0;
     tinfo[threadIdx.x] = info;
   }
   __syncthreads();
@@ -334,7 +347,7 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
         return (crank == 0 ? (uint32_t)(kEpiThreads * 4 * nparts) : 0u) + (t + 1 < H ? (uint32_t)(kEpiThreads * 16) : 0u);
       };
       const uint32_t xbar = smem_u32(&bars[1 + NTILES]);
-      if (PAIR && tis.valid && crank != 0) {
+      if (PAIR && tis.valid && crank != 0 && late_gate(tis)) {
         // CTA 1 keeps no objective: its scorer warp only re-arms the two exchange barriers, each for the
         // step after next once the current one has completed
         for (int ts = -1; ts + 1 < H; ++ts) {
@@ -357,7 +370,8 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
           for (int f = 0; f < 7; ++f) my_rs[f * 128 + 32 * i] = 0u;
           my_rs[7 * 128 + 32 * i] = row < tis.count ? (uint32_t)decode_row(g, tis.member, tis.k0 + row).out : 0xffffffffu;
         }
-        for (int ts = -1; ts < H; ++ts) {                                  // ts = -1: distance / cost of s_0
+        const bool live = late_gate(tis);
+        for (int ts = -1; live && ts < H; ++ts) {                          // ts = -1: distance / cost of s_0
           named_bar_sync_n(kBarPart + j, tile_bar_threads);
           const float* part_tile = part_tile0;
           if (PAIR) {                                                      // + the peer CTA's slices of this step
@@ -393,7 +407,7 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
           }
           if (ts + 1 < H) named_bar_arrive_n(kBarFree + j, tile_bar_threads);
         }
-        if (prm.row_return != nullptr) {
+        if (live && prm.row_return != nullptr) {
 #pragma unroll 1
           for (int i = 0; i < n_quarters; ++i) {
             const uint32_t* q = my_rs + 32 * i;
@@ -418,7 +432,8 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
 #ifdef SIMBA_TC_TIMELINE
         const int tl_who = (j == 0 && lane == 0) ? 2 : -1;
 #endif
-        for (int t = 0; t < H; ++t) {
+        const bool live = late_gate(tinfo[j]);
+        for (int t = 0; live && t < H; ++t) {
 #ifdef SIMBA_TC_TIMELINE
           const int tl_t = t;
 #endif
@@ -587,8 +602,17 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
           }
           noise.put4_dyn(b, z);
         };
+        // PAIR: s_0 does not depend on the previous kernel — its loads are in flight across the dependency wait
+        float s0v[8];
+        if constexpr (PAIR) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s0v[i] = (row_ok && hc.o_base + i < O) ? s0_ptr[hc.o_base + i] : 0.0f;
+        }
+        const bool live = late_gate(ti);
+        if (live) {
         prefetch_actions(0);
-        head_first_pass<OW>(hc, astore, s0_ptr, row_ok, act_pf);
+        if constexpr (PAIR) head_first_pass_vals(hc, astore, s0v, act_pf);
+        else head_first_pass<OW>(hc, astore, s0_ptr, row_ok, act_pf);
         prefetch_actions(1);
         exchange(-1, true);
         publish_a();                                        // layer-0 input of step 0
@@ -672,6 +696,7 @@ __global__ void __launch_bounds__(kBoundThreads, 1) rollout_tc_kernel(const Roll
           if (keeps_score) named_bar_arrive_n(kBarPart + j, tile_bar_threads);  // partial minima of s_{t+1} published (scorer warp)
           TL(42);
         }
+        }  // live
       }
     }
   }

@@ -236,6 +236,30 @@ __device__ __forceinline__ void head_first_pass(const HeadCtx& c, const AStore& 
   head_publish(c, gmin, cmin);
 }
 
+// The same for a thread that owns one 8-wide chunk and already holds its eight s_0 values (zero beyond O or
+// for a padding row) in registers: rollout_tc.cu's CTA-pair variant loads them before the dependency wait.
+template <class AStore>
+__device__ __forceinline__ void head_first_pass_vals(const HeadCtx& c, const AStore& astore, const float (&s0v)[8],
+                                                     const float (&act0)[4]) {
+  float gmin = INFINITY, cmin[SIMBA_MAX_CONSTRAINTS];
+#pragma unroll
+  for (int q = 0; q < SIMBA_MAX_CONSTRAINTS; ++q) cmin[q] = INFINITY;
+  const int oc = c.o_base;
+  float sv[8];
+  uint32_t st[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sv[i] = s0v[i];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+      if (oc + i == c.O + a) sv[i] = act0[a];             // a_0 (zero beyond A)
+    st[i] = __float_as_uint(sv[i]);
+  }
+  tmem_st<8>(c.t_state + oc, st);
+  head_chunk_tail(c, astore, oc, c.slice_bits & 31u, sv, true, gmin, cmin);
+  head_publish(c, gmin, cmin);
+}
+
 // Step t: s_{t+1} = s_t + mu (+ sqrt(softplus(raw var) + 1e-4) * eps), state back to TMEM, scaled bf16
 // x_{t+1} into the A operand, partial lidar minima of s_{t+1} published. Padded outputs (o >= O) have
 // zero weights, zero bias and zero noise, so their delta is exactly 0 and needs no mask.
