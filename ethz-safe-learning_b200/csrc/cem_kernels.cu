@@ -649,8 +649,8 @@ cudaError_t launch_select_elites(const SelectParams& p, cudaStream_t st) {
 constexpr int kRefitThreads = 1024;
 
 #ifdef SIMBA_TC_TIMELINE
-__device__ long long* g_utl_ptr = nullptr;          // set by thread 0 of the fused update kernel (debug stamps)
-#define RTL(k) do { if (blockIdx.x == 0 && threadIdx.x == 0 && g_utl_ptr != nullptr) g_utl_ptr[k] = clock64(); } while (0)
+__shared__ long long* s_rtl_ptr;                    // set by thread 0 of the kernels that call refit_body (debug stamps)
+#define RTL(k) do { if (blockIdx.x == 0 && threadIdx.x == 0 && s_rtl_ptr != nullptr) s_rtl_ptr[k] = clock64(); } while (0)
 #else
 #define RTL(k) do { } while (0)
 #endif
@@ -779,6 +779,9 @@ __global__ void __launch_bounds__(kRefitThreads) refit_kernel(RefitParams p) {
   const int s = blockIdx.x;
   if (p.active != nullptr && p.active[s] == 0) return;
   extern __shared__ float sh[];           // [groups][HA] partials, then [HA] mean, [HA] sigma
+#ifdef SIMBA_TC_TIMELINE
+  if (threadIdx.x == 0) s_rtl_ptr = nullptr;
+#endif
   refit_body(p, s, p.elite + (long)s * p.K, sh);
 }
 
@@ -1053,7 +1056,7 @@ __global__ void __launch_bounds__(kRefitThreads) cem_update_kernel(UpdateParams 
   asm volatile("griddepcontrol.wait;" ::: "memory");
   UTL(1);
 #ifdef SIMBA_TC_TIMELINE
-  if (blockIdx.x == 0 && threadIdx.x == 0) g_utl_ptr = u.timeline;
+  if (threadIdx.x == 0) s_rtl_ptr = u.timeline;       // only thread 0 reads it back
 #endif
   // ---- every load whose address is known, unconditionally and at once --------------------------------
   const bool active = u.refit.active == nullptr || u.refit.active[s] != 0;
