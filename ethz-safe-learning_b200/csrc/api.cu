@@ -1056,9 +1056,11 @@ static int enqueue_plan(simba_planner* p, cudaStream_t st, int* n_launches) {
     if (rc) return rc; ++launches;
     for (int it = 0; it < c.iterations; ++it) {
       const float* eps = p->ext_eps ? p->ext_eps + (size_t)it * S * c.horizon * B * O : nullptr;
-      // the first rollout follows the plain sample kernel; later ones follow a PDL-aware update kernel
+      // every rollout is a programmatic dependent launch: the first one's prologue (barriers, TMEM, the weight
+      // copies, tables) overlaps the sample kernel, which triggers its dependents at once; later ones overlap the
+      // update kernel. The rollout's dependency wait covers the full completion of the kernel before it.
       rc = do_rollout_score(p, p->d_states, p->actions, eps, 0, sp, it, p->active, p->row_ret,
-                            p->row_cmask, p->row_csum, st, p->use_pdl && it > 0);
+                            p->row_cmask, p->row_csum, st, p->use_pdl);
       if (rc) return rc; ++launches;
       UpdateParams u{};
       u.pdl = p->use_pdl ? 1 : 0;

@@ -97,6 +97,9 @@ __device__ __forceinline__ bool sampled_here(const SampleParams& p, int i) {
 }
 
 __global__ void __launch_bounds__(256) sample_actions_kernel(SampleParams p) {
+  // a rollout launched behind this kernel as a programmatic dependent may start its prologue now (it waits
+  // for this grid's completion before it reads the actions); a no-op for plain launches
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int JB = (p.H * p.A + 3) >> 2;
   const int NC = p.n_cand ? p.n_cand : p.N;     // candidates this rank samples
   const long total = (long)p.S * NC * JB;
@@ -687,36 +690,21 @@ __device__ __forceinline__ void refit_body(const RefitParams& p, int s, const in
   if (tid == 0 && p.iterations_run != nullptr) iters_old = p.iterations_run[s];
 
   const int grp = div_small(tid, HA, 1.0f / (float)HA), c = tid - grp * HA;   // HA <= 1024 (checked at creation)
-  // Small elite sets (K <= 8 groups: the fused update of a single plan): a thread's at most eight gathered
-  // values stay in registers for the second pass. Same values, same accumulation order (k ascending).
   RTL(10);
-  const bool small = p.K <= 8 * groups;
-  const int umax = small ? (p.K + groups - 1) / groups : 0;   // uniform: gathers per thread (1 for a single plan's K = 15)
-  const bool works = grp < groups && grp < p.K;               // this thread's group holds at least one elite
-  float held[8];
-  if (small && works) {
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      if (u < umax) {                                          // uniform branch: idle iterations are skipped, not predicated
-        const int k = grp + u * groups;
-        held[u] = 0.0f;
-        if (k < p.K) held[u] = acts_copy != nullptr ? acts_copy[elite[k] * HA + c] : acts[(long)elite[k] * HA + c];
-      }
-    }
-  }
+  // A single plan's elite set (K <= groups: one elite per row group at most) keeps the thread's one gathered
+  // value in a register for the second pass. Same values, same accumulation order as the general loop below —
+  // and a fraction of its code: this function runs once per launch, i.e. out of a cold instruction cache.
+  const bool single = p.K <= groups;
+  const bool works = grp < p.K;                                // this thread's group holds an elite (single only)
+  float held = 0.0f;
+  if (single && works) held = acts_copy != nullptr ? acts_copy[elite[grp] * HA + c] : acts[(long)elite[grp] * HA + c];
   for (int pass = 0; pass < 2; ++pass) {
     if (grp < groups) {
       float acc = 0.0f;
-      if (small) {
+      if (single) {
         if (works) {
-          const float m = pass ? mean[c] : 0.0f;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            if (u < umax && grp + u * groups < p.K) {
-              if (pass) { const float d = __fsub_rn(held[u], m); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
-              else acc = __fadd_rn(acc, held[u]);
-            }
-          }
+          if (pass) { const float d = __fsub_rn(held, mean[c]); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
+          else acc = __fadd_rn(acc, held);
         }
       } else {
         const float m = pass ? mean[c] : 0.0f;
@@ -1031,7 +1019,7 @@ __global__ void __launch_bounds__(kRefitThreads) cem_update_kernel(UpdateParams 
   __shared__ int sh_total;
   __shared__ int sh_stopped;
   const bool staged = u.stage != 0;
-  const bool presample = staged && !u.last && u.sample.z == nullptr;
+  const bool presample = staged && !u.last;           // Philox draws, or the externally supplied ones (parity mode)
   // the plan's seed is uploaded before the plan's first kernel, which is a full dependency of everything here
   const uint64_t seed_now = u.sample.seed_ptr ? *u.sample.seed_ptr : u.sample.seed;
   if (presample) {
@@ -1234,7 +1222,7 @@ __global__ void __launch_bounds__(kRefitThreads) cem_update_kernel(UpdateParams 
       for (int idx = tid; idx < N * JB; idx += kRefitThreads) {
         const int i = div_small(idx, JB, inv_JB), j = idx - i * JB;
         float z[4], out[4];
-        if (presample) {
+        if (staged) {                                     // draws made before the dependency wait
           const float4 zz = *reinterpret_cast<const float4*>(z_sm + 4 * idx);
           z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
         } else {
