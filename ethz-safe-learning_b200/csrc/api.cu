@@ -1046,14 +1046,15 @@ static int enqueue_plan(simba_planner* p, cudaStream_t st, int* n_launches) {
   memcpy(ip.init_stddev, c.init_stddev, sizeof(ip.init_stddev));
   ip.mu = p->mu; ip.sigma = p->sigma; ip.best_action = p->best_action; ip.best_score = p->best_score;
   ip.active = p->active; ip.iterations_run = p->iters;
-  CUDA_TRY(launch_plan_init(ip, st)); ++launches;
   const bool multi = c.world_size > 1;
   float* pairs_all = multi ? p->pairs_all : p->pairs_local;
+  if (!p->fused_update) { CUDA_TRY(launch_plan_init(ip, st)); ++launches; }
   if (p->fused_update) {
-    // small population on one rank: sample(0), then per iteration rollout + one fused update kernel
+    // small population on one rank: init + sample(0) in one launch, then per iteration rollout + one fused update kernel
     const float* z0 = p->ext_z_actions;
-    int rc = do_sample_actions(p, p->mu, p->sigma, z0, 0, sp, 0, p->active, p->actions, st);
-    if (rc) return rc; ++launches;
+    const SampleParams sp0 = make_sample_params(p, p->mu, p->sigma, z0, 0, sp, 0, p->active, p->actions);
+    CUDA_TRY(launch_plan_begin(ip, sp0, st)); ++launches;
+    int rc = SIMBA_OK;
     for (int it = 0; it < c.iterations; ++it) {
       const float* eps = p->ext_eps ? p->ext_eps + (size_t)it * S * c.horizon * B * O : nullptr;
       // every rollout is a programmatic dependent launch: the first one's prologue (barriers, TMEM, the weight
@@ -1150,7 +1151,7 @@ static int upload_seed(simba_planner* p, uint64_t seed, cudaStream_t st) {
 extern "C" int simba_planner_launches_per_plan(simba_planner_t* p, int32_t* out) {
   if (!p || !out) return fail(SIMBA_ERR_BAD_CONFIG, "null argument");
   const int per_iter = 5 + (p->cfg.world_size > 1 ? 1 : 0);
-  *out = p->fused_update ? 2 + 2 * p->cfg.iterations : 1 + per_iter * p->cfg.iterations + 2;
+  *out = p->fused_update ? 1 + 2 * p->cfg.iterations : 1 + per_iter * p->cfg.iterations + 2;
   return SIMBA_OK;
 }
 

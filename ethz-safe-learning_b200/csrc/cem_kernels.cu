@@ -1312,6 +1312,51 @@ __global__ void plan_init_kernel(PlanInitParams p) {
   }
 }
 
+// plan_init + the first iteration's sampling in one launch (the fused single-rank plan): mu / sigma of iteration 0
+// are the initial mean / stddev per action dimension, so no thread has to read what another one initialises
+__global__ void __launch_bounds__(256) plan_begin_kernel(PlanInitParams ip, SampleParams sp) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the first rollout's prologue may start
+  __shared__ float mu0[1024], sg0[1024];                            // H * A <= 1024 (checked at creation)
+  const int HA = ip.H * ip.A;
+  for (int e = threadIdx.x; e < HA; e += blockDim.x) {
+    mu0[e] = ip.init_mean[e % ip.A];
+    sg0[e] = ip.init_stddev[e % ip.A];
+  }
+  const long gtid = blockIdx.x * (long)blockDim.x + threadIdx.x, gsize = (long)gridDim.x * blockDim.x;
+  for (long idx = gtid; idx < (long)ip.S * HA; idx += gsize) {
+    const int a = (int)(idx % HA) % ip.A;
+    ip.mu[idx] = ip.init_mean[a];
+    ip.sigma[idx] = ip.init_stddev[a];
+  }
+  for (long idx = gtid; idx < (long)ip.S * ip.A; idx += gsize) ip.best_action[idx] = 0.0f;
+  for (long idx = gtid; idx < ip.S; idx += gsize) {
+    ip.best_score[idx] = -INFINITY;
+    ip.active[idx] = 1;
+    ip.iterations_run[idx] = 0;
+  }
+  __syncthreads();
+  const uint64_t seed = sp.seed_ptr ? *sp.seed_ptr : sp.seed;
+  const int JB = (HA + 3) >> 2;
+  const long total = (long)sp.S * sp.N * JB;
+  for (long idx = gtid; idx < total; idx += gsize) {
+    const int j = (int)(idx % JB);
+    const long si = idx / JB;
+    const int s = (int)(si / sp.N), i = (int)(si - (long)s * sp.N);
+    float out[4];
+    sample_values4_from(sp, mu0, sg0, seed, s, i, j, out);
+    store_block4(sp, s, i, j, out, sp.out);
+  }
+}
+
+cudaError_t launch_plan_begin(const PlanInitParams& ip, const SampleParams& sp, cudaStream_t st) {
+  const long total = (long)sp.S * sp.N * ((sp.H * sp.A + 3) / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  plan_begin_kernel<<<blocks, 256, 0, st>>>(ip, sp);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_plan_init(const PlanInitParams& p, cudaStream_t st) {
   const int n = p.S * p.H * p.A;
   plan_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(p);

@@ -97,6 +97,7 @@ struct UpdateParams {                 // fused k8 + k9 + k10 (+ next k1 | k11): 
 };
 
 cudaError_t launch_cem_update(const UpdateParams& u, cudaStream_t st);
+cudaError_t launch_plan_begin(const PlanInitParams& ip, const SampleParams& sp, cudaStream_t st);
 cudaError_t launch_sample_actions(const SampleParams& p, cudaStream_t st);
 cudaError_t launch_score_reduce(const ReduceParams& p, cudaStream_t st);
 cudaError_t launch_select_elites(const SelectParams& p, cudaStream_t st);
