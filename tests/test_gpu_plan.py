@@ -185,6 +185,21 @@ def test_fused_update_kernel_is_bit_identical_to_separate_kernels(case):
     assert np.array_equal(f[5], u[5]) and np.all(f[5] >= 1) and np.all(f[5] <= c['I'])
 
 
+def test_repeated_c1_plans_are_bit_identical():
+    """The production path (bf16, device Philox, CUDA graph, programmatic dependent launches, the two-CTA rollout
+    with its DSMEM exchange, the staged update kernel) replayed 300 times with one seed: any race in the
+    hand-offs shows up as a differing action or score."""
+    c = helpers.workload('c1')
+    pol = helpers.cuda_policy(c, 'penalty', precision='bf16')
+    a0, s0 = pol.do_generate_action(c['state'], seed=77)
+    a0, s0 = np.array(a0).copy(), float(np.asarray(s0))
+    for _ in range(300):
+        a, s = pol.do_generate_action(c['state'], seed=77)
+        assert np.array_equal(a0, a) and s0 == float(np.asarray(s))
+    a1, _ = pol.do_generate_action(c['state'], seed=78)
+    assert not np.array_equal(a0, a1)
+
+
 def test_wide_model_c5_reward_only_vs_safety_aware():
     """BASELINE configs[4]: 10-member ensemble, 4x400 hidden, horizon 50, on the fp32 kernel (exact
     parity contract). Widths neither tcgen05 kernel covers (> 416) report SIMBA_ERR_UNSUPPORTED for bf16."""
