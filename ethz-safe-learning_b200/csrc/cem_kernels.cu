@@ -963,6 +963,9 @@ __host__ __device__ inline size_t update_stage_bytes(int P, int N, int HA) {
   return rows * 16 + (size_t)N * HA * 4 + (size_t)N * JB * 16 + (size_t)N * 8 + (size_t)(HA + 4) * 8 + (size_t)N * 64 + 96;
 }
 
+// STAGED is a template parameter so that the kernel a single plan runs carries none of the fallback code
+// (it executes once per launch, out of a cold instruction cache: code size is latency).
+template <bool STAGED>
 __global__ void __launch_bounds__(kRefitThreads) cem_update_kernel(UpdateParams u) {
   UTL(0);
   // PDL: the next rollout may start its prologue (TMEM allocation, barrier init) now.
@@ -1018,7 +1021,7 @@ __global__ void __launch_bounds__(kRefitThreads) cem_update_kernel(UpdateParams 
   __shared__ int warp_sums[32];
   __shared__ int sh_total;
   __shared__ int sh_stopped;
-  const bool staged = u.stage != 0;
+  constexpr bool staged = STAGED;
   const bool presample = staged && !u.last;           // Philox draws, or the externally supplied ones (parity mode)
   // the plan's seed is uploaded before the plan's first kernel, which is a full dependency of everything here
   const uint64_t seed_now = u.sample.seed_ptr ? *u.sample.seed_ptr : u.sample.seed;
@@ -1279,7 +1282,7 @@ cudaError_t launch_cem_update(const UpdateParams& u_in, cudaStream_t st) {
   u.stage = (smem + stage + 1024 <= 200 * 1024 && u.select.N <= kRefitThreads) ? 1 : 0;
   if (u.stage) smem += stage;
   {
-    cudaError_t e = cudaFuncSetAttribute(cem_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(cem_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
   }
   cudaLaunchConfig_t cfg{};
@@ -1292,7 +1295,7 @@ cudaError_t launch_cem_update(const UpdateParams& u_in, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = u.pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, cem_update_kernel, u);
+  return u.stage ? cudaLaunchKernelEx(&cfg, cem_update_kernel<true>, u) : cudaLaunchKernelEx(&cfg, cem_update_kernel<false>, u);
 }
 
 // plan bookkeeping: reset mu/sigma/best/active at the start of a plan (cem_mpc.py:36-42)
