@@ -32,5 +32,7 @@ for it in range(c['I']):
     r = t[3, 10 + it]          # rollout: 0 entry, 1 setup done, 2 wait passed, 3 first A, 4 items done, 5 exit
     uu = t[3, 1 + it][32:]     # update: 0 entry, 1 wait passed, 6 end
     base = t[3, 10][2]
-    print("iteration %d: rollout wait passed %7d, first A %7d, items done %7d, exit %7d | update wait passed %7d, end %7d"
-          % (it, r[2] - base, r[3] - base, r[4] - base, r[5] - base, uu[1] - base, uu[6] - base))
+    print("iteration %d: rollout wait passed %7d, first A %7d, last step done %7d, items done %7d, exit %7d | update wait passed %7d, end %7d"
+          % (it, r[2] - base, r[3] - base, r[6] - base, r[4] - base, r[5] - base, uu[1] - base, uu[6] - base))
+print("== rollout step lengths inside the plan (cycles; epilogue warp 0 of CTA 0, last launch): step 0 .. H-2")
+print(' '.join(str(int(t[0, k + 1][0] - t[0, k][0])) for k in range(c['H'] - 1)))
