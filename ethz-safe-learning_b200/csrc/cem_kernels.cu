@@ -763,6 +763,50 @@ __device__ __forceinline__ void refit_body(const RefitParams& p, int s, const in
   }
 }
 
+// refit_body for an elite set with at most one elite per row group (K <= groups: a single plan's K = 15 against 34
+// groups), on the staged actions of the fused update kernel. In that case refit_body's partial of group g is
+// 0 + x_g (pass 0) or 0 + (x_g - mean)^2 (pass 1) for g < K and 0 for the idle groups, summed over the groups in
+// ascending order — which one thread per column can do directly: the same additions in the same order, without
+// the [groups][H A] partials, their four CTA barriers and the (group, column) thread layout.
+__device__ __forceinline__ void refit_single(const RefitParams& p, int s, const int* elite, const float* acts_s,
+                                             float* mean, float* sig, int* stopped_sh, float mu_old, float sg_old,
+                                             int iters_old) {
+  const int HA = p.H * p.A, groups = p.groups, K = p.K, tid = threadIdx.x;
+  const float kf = (float)K;
+  if (tid < HA) {
+    const int c = tid;
+    float tot = 0.0f;
+    for (int gI = 0; gI < groups; ++gI) {
+      float a = 0.0f;
+      if (gI < K) a = __fadd_rn(0.0f, acts_s[elite[gI] * HA + c]);
+      tot = __fadd_rn(tot, a);
+    }
+    const float m = __fdiv_rn(tot, kf);
+    float tot2 = 0.0f;
+    for (int gI = 0; gI < groups; ++gI) {
+      float a = 0.0f;
+      if (gI < K) { const float d = __fsub_rn(acts_s[elite[gI] * HA + c], m); a = __fadd_rn(0.0f, __fmul_rn(d, d)); }
+      tot2 = __fadd_rn(tot2, a);
+    }
+    const float sd = sqrtf(__fdiv_rn(tot2, kf));                          // cem_mpc.py:63
+    const float mu_new = __fadd_rn(__fmul_rn(p.smoothing, mu_old), __fmul_rn(p.one_minus_smoothing, m));
+    const float sg_new = __fadd_rn(__fmul_rn(p.smoothing, sg_old), __fmul_rn(p.one_minus_smoothing, sd));
+    p.mu[s * HA + c] = mu_new;                                            // cem_mpc.py:64-65
+    p.sigma[s * HA + c] = sg_new;
+    sig[c] = sg_new;
+    mean[c] = mu_new;               // the next iteration is sampled from these copies
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float tot = 0.0f;
+    for (int cc = 0; cc < HA; ++cc) tot = __fadd_rn(tot, sig[cc]);
+    if (p.iterations_run != nullptr) p.iterations_run[s] = iters_old + 1;
+    const bool stop = p.active != nullptr && __fdiv_rn(tot, (float)HA) <= p.stddev_threshold;  // cem_mpc.py:66-67
+    if (stop) p.active[s] = 0;
+    *stopped_sh = stop ? 1 : 0;
+  }
+}
+
 __global__ void __launch_bounds__(kRefitThreads) refit_kernel(RefitParams p) {
   const int s = blockIdx.x;
   if (p.active != nullptr && p.active[s] == 0) return;
@@ -1052,6 +1096,11 @@ __global__ void __launch_bounds__(kRefitThreads) cem_update_kernel(UpdateParams 
   // ---- every load whose address is known, unconditionally and at once --------------------------------
   const bool active = u.refit.active == nullptr || u.refit.active[s] != 0;
   const float best_prev = u.select.best_score[s];
+  const bool refit_one = staged && K <= groups;       // refit_single: its mu / sigma / counter loads ride along here
+  float mu_old = 0.0f, sg_old = 0.0f;
+  int iters_old = 0;
+  if (refit_one && tid < HA) { mu_old = u.refit.mu[s * HA + tid]; sg_old = u.refit.sigma[s * HA + tid]; }
+  if (refit_one && tid == 0 && u.refit.iterations_run != nullptr) iters_old = u.refit.iterations_run[s];
   if (staged) {
     // batches of four elements per thread and array: all loads of a batch are in flight before the first store
     const float* gret = u.reduce.row_return + (long)s * rows;
@@ -1213,7 +1262,9 @@ __global__ void __launch_bounds__(kRefitThreads) cem_update_kernel(UpdateParams 
     __syncthreads();
     UTL(4);
     // ---- k10: refit (also clears active[s] when the stddev threshold is met) --------------------
-    refit_body(u.refit, s, elite_sh, sh, &sh_stopped, staged ? act_sm : nullptr);
+    if (refit_one) refit_single(u.refit, s, elite_sh, act_sm, sh + groups * HA, sh + (groups + 1) * HA, &sh_stopped, mu_old,
+                                sg_old, iters_old);
+    else refit_body(u.refit, s, elite_sh, sh, &sh_stopped, staged ? act_sm : nullptr);
     __syncthreads();
     UTL(5);
   }
