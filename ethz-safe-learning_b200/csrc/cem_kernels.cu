@@ -769,25 +769,44 @@ __device__ __forceinline__ void refit_body(const RefitParams& p, int s, const in
 // ascending order — which one thread per column can do directly: the same additions in the same order, without
 // the [groups][H A] partials, their four CTA barriers and the (group, column) thread layout.
 __device__ __forceinline__ void refit_single(const RefitParams& p, int s, const int* elite, const float* acts_s,
-                                             float* mean, float* sig, int* stopped_sh, float mu_old, float sg_old,
-                                             int iters_old) {
+                                             float* xs, float* mean, float* sig, int* stopped_sh, float mu_old,
+                                             float sg_old, int iters_old) {
   const int HA = p.H * p.A, groups = p.groups, K = p.K, tid = threadIdx.x;
   const float kf = (float)K;
+  RTL(10);
+  // the K elite rows, gathered by K * HA threads at once into xs[K][HA] (the idle partials area), so that the
+  // column threads below read plain rows: no dependent index -> value round trip inside their addition chains
+  for (int i = tid; i < K * HA; i += kRefitThreads) {
+    const int gI = div_small(i, HA, 1.0f / (float)HA);
+    xs[i] = acts_s[elite[gI] * HA + (i - gI * HA)];
+  }
+  __syncthreads();
+  RTL(11);
   if (tid < HA) {
     const int c = tid;
-    float tot = 0.0f;
-    for (int gI = 0; gI < groups; ++gI) {
-      float a = 0.0f;
-      if (gI < K) a = __fadd_rn(0.0f, acts_s[elite[gI] * HA + c]);
-      tot = __fadd_rn(tot, a);
+    float tot = 0.0f, tot2 = 0.0f;
+    for (int g0 = 0; g0 < K; g0 += 8) {                       // eight independent reads, then their additions
+      float x[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) x[q] = xs[min(g0 + q, K - 1) * HA + c];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (g0 + q < K) tot = __fadd_rn(tot, __fadd_rn(0.0f, x[q]));
     }
+    for (int gI = K; gI < groups; ++gI) tot = __fadd_rn(tot, 0.0f);      // the idle groups' partials
     const float m = __fdiv_rn(tot, kf);
-    float tot2 = 0.0f;
-    for (int gI = 0; gI < groups; ++gI) {
-      float a = 0.0f;
-      if (gI < K) { const float d = __fsub_rn(acts_s[elite[gI] * HA + c], m); a = __fadd_rn(0.0f, __fmul_rn(d, d)); }
-      tot2 = __fadd_rn(tot2, a);
+    for (int g0 = 0; g0 < K; g0 += 8) {
+      float x[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) x[q] = xs[min(g0 + q, K - 1) * HA + c];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float d = __fsub_rn(x[q], m);
+        if (g0 + q < K) tot2 = __fadd_rn(tot2, __fadd_rn(0.0f, __fmul_rn(d, d)));
+      }
     }
+    for (int gI = K; gI < groups; ++gI) tot2 = __fadd_rn(tot2, 0.0f);
+    RTL(12);
     const float sd = sqrtf(__fdiv_rn(tot2, kf));                          // cem_mpc.py:63
     const float mu_new = __fadd_rn(__fmul_rn(p.smoothing, mu_old), __fmul_rn(p.one_minus_smoothing, m));
     const float sg_new = __fadd_rn(__fmul_rn(p.smoothing, sg_old), __fmul_rn(p.one_minus_smoothing, sd));
@@ -796,15 +815,29 @@ __device__ __forceinline__ void refit_single(const RefitParams& p, int s, const 
     sig[c] = sg_new;
     mean[c] = mu_new;               // the next iteration is sampled from these copies
   }
+  RTL(13);
   __syncthreads();
-  if (tid == 0) {
+  RTL(14);
+  if (tid < 32) {
+    // mean(sigma) in column order: one read per lane, lane 0 takes the values through shuffles, so only the
+    // additions are a dependent chain
     float tot = 0.0f;
-    for (int cc = 0; cc < HA; ++cc) tot = __fadd_rn(tot, sig[cc]);
-    if (p.iterations_run != nullptr) p.iterations_run[s] = iters_old + 1;
-    const bool stop = p.active != nullptr && __fdiv_rn(tot, (float)HA) <= p.stddev_threshold;  // cem_mpc.py:66-67
-    if (stop) p.active[s] = 0;
-    *stopped_sh = stop ? 1 : 0;
+    for (int c0 = 0; c0 < HA; c0 += 32) {
+      const float mine = c0 + tid < HA ? sig[c0 + tid] : 0.0f;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const float v = __shfl_sync(0xffffffffu, mine, q);
+        if (c0 + q < HA) tot = __fadd_rn(tot, v);
+      }
+    }
+    if (tid == 0) {
+      if (p.iterations_run != nullptr) p.iterations_run[s] = iters_old + 1;
+      const bool stop = p.active != nullptr && __fdiv_rn(tot, (float)HA) <= p.stddev_threshold;  // cem_mpc.py:66-67
+      if (stop) p.active[s] = 0;
+      *stopped_sh = stop ? 1 : 0;
+    }
   }
+  RTL(15);
 }
 
 __global__ void __launch_bounds__(kRefitThreads) refit_kernel(RefitParams p) {
@@ -1262,8 +1295,8 @@ __global__ void __launch_bounds__(kRefitThreads) cem_update_kernel(UpdateParams 
     __syncthreads();
     UTL(4);
     // ---- k10: refit (also clears active[s] when the stddev threshold is met) --------------------
-    if (refit_one) refit_single(u.refit, s, elite_sh, act_sm, sh + groups * HA, sh + (groups + 1) * HA, &sh_stopped, mu_old,
-                                sg_old, iters_old);
+    if (refit_one) refit_single(u.refit, s, elite_sh, act_sm, sh, sh + groups * HA, sh + (groups + 1) * HA, &sh_stopped,
+                                mu_old, sg_old, iters_old);
     else refit_body(u.refit, s, elite_sh, sh, &sh_stopped, staged ? act_sm : nullptr);
     __syncthreads();
     UTL(5);

@@ -25,7 +25,7 @@ for it in range(c['I']):
     print("   detail (cycles after the wait): loads issued %d, staged %d, scores done (thread 0) %d | refit: start %d, "
           % tuple(ev[k] - ev[1] for k in (7, 8, 9, 10))
           + ', '.join("pass%d part %d sync %d totals %d sync %d" % ((ps,) + tuple(ev[11 + 4 * ps + q] - ev[1] for q in range(4)))
-                      for ps in range(2)))
+                      for ps in range(2)) + " | refit_single stamps 10..15: " + ' '.join(str(int(ev[k] - ev[1])) for k in range(10, 16)))
 
 print("== plan anatomy, ns on the global timer (rollout: thread 0 of CTA 0; update: thread 0)")
 for it in range(c['I']):
