@@ -345,7 +345,7 @@ def main():
                                       {"parallelism": "independent plans per GPU (no collective)" if world > 1 else "1 GPU"}),
             "transitions_per_s": world * K * iters_total * c['H'] * B / t_dev,
             "iterations_run_per_plan": iters_total,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": c['O'] * 4 + 8,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": c['O'] * 4 + 16,
                     "d2h_bytes_per_step": c['A'] * 4 + 8},
             "gpu_launches": launches, "launches_per_plan": pol.launches_per_plan,
             "clocks": clocks, "roofline": roofline, "wall_s_timed_loop": t_wall}

@@ -605,6 +605,9 @@ struct simba_planner {
   uint64_t* h_seed_ring = nullptr;     // pinned
   int seed_slot = 0;
   float* h_out = nullptr;              // pinned: [S*A action][S score][S iters(int)]
+  uint8_t* h_in = nullptr;             // pinned: [seed (16 bytes)][S*O states] of a plan_host() call
+  uint8_t* d_in = nullptr;             // device: the same block; d_seed and d_states point into it
+  float* d_out = nullptr;              // device: [S*A action][S score][S iters(int)]; the d_out_* pointers point into it
   const float *ext_z_actions = nullptr, *ext_eps = nullptr, *ext_z_final = nullptr;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t plan_done = nullptr;   // recorded after every plan: the next plan (any stream) waits on it
@@ -664,10 +667,9 @@ static void planner_free(simba_planner* p) {
   cudaFree(p->d_tiles); cudaFree(p->actions); cudaFree(p->row_ret); cudaFree(p->row_csum);
   cudaFree(p->pairs_local); cudaFree(p->pairs_all); cudaFree(p->mu); cudaFree(p->sigma);
   cudaFree(p->best_action); cudaFree(p->best_score); cudaFree(p->scores); cudaFree(p->row_cmask); cudaFree(p->key_scratch);
-  cudaFree(p->elite); cudaFree(p->active); cudaFree(p->iters); cudaFree(p->d_states);
-  cudaFree(p->d_out_action); cudaFree(p->d_out_score); cudaFree(p->d_out_iters);
-  cudaFree(p->d_seed);
-  cudaFreeHost(p->h_seed_ring); cudaFreeHost(p->h_out);
+  cudaFree(p->elite); cudaFree(p->active); cudaFree(p->iters);
+  cudaFree(p->d_in); cudaFree(p->d_out);           // d_seed / d_states and d_out_* are interior pointers
+  cudaFreeHost(p->h_seed_ring); cudaFreeHost(p->h_out); cudaFreeHost(p->h_in);
 }
 
 extern "C" int simba_planner_destroy(simba_planner_t* p) {
@@ -775,16 +777,21 @@ extern "C" int simba_planner_create(simba_model_t* model, const simba_planner_co
   PL_ALLOC(p->elite, S * (size_t)cfg->n_elite * 4);
   PL_ALLOC(p->active, S * 4);
   PL_ALLOC(p->iters, S * 4);
-  PL_ALLOC(p->d_states, S * O * 4);
-  PL_ALLOC(p->d_out_action, S * A * 4);
-  PL_ALLOC(p->d_out_score, S * 4);
-  PL_ALLOC(p->d_out_iters, S * 4);
-  PL_ALLOC(p->d_seed, 8);
+  // one input block (seed + states) and one output block (action, score, iterations): a host-buffer plan is one
+  // copy in and one copy out around the graph
+  PL_ALLOC(p->d_in, 16 + S * O * 4);
+  p->d_seed = reinterpret_cast<uint64_t*>(p->d_in);
+  p->d_states = reinterpret_cast<float*>(p->d_in + 16);
+  PL_ALLOC(p->d_out, S * (A + 2) * 4);
+  p->d_out_action = p->d_out;
+  p->d_out_score = p->d_out + S * A;
+  p->d_out_iters = reinterpret_cast<int32_t*>(p->d_out + S * A + S);
 #undef PL_ALLOC
   if (cudaMemcpy(p->d_tiles, p->tiles.data(), p->tiles.size() * sizeof(Tile),
                  cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMallocHost((void**)&p->h_seed_ring, 64 * sizeof(uint64_t)) != cudaSuccess ||
       cudaMallocHost((void**)&p->h_out, S * (A + 2) * 4) != cudaSuccess ||
+      cudaMallocHost((void**)&p->h_in, 16 + S * O * 4) != cudaSuccess ||
       cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&p->plan_done, cudaEventDisableTiming) != cudaSuccess) {
     planner_free(p); delete p;
@@ -1191,16 +1198,16 @@ extern "C" int simba_plan_host(simba_planner_t* p, const float* states_host, uin
   int rc = ensure_graph(p);
   if (rc != SIMBA_OK) return rc;
   if (p->plan_done) CUDA_TRY(cudaStreamWaitEvent(st, p->plan_done, 0));    // behind a plan_device() on another stream
-  rc = upload_seed(p, seed, st);
-  if (rc != SIMBA_OK) return rc;
-  CUDA_TRY(cudaMemcpyAsync(p->d_states, states_host, S * O * 4, cudaMemcpyHostToDevice, st));
+  // seed + states staged in pinned memory: one host-to-device copy (the call is synchronous, so one staging
+  // block is enough), the graph, one device-to-host copy of the three results
+  memcpy(p->h_in, &seed, sizeof(seed));
+  memcpy(p->h_in + 16, states_host, S * O * 4);
+  CUDA_TRY(cudaMemcpyAsync(p->d_in, p->h_in, 16 + S * O * 4, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaGraphLaunch(p->graph_exec, st));
   float* h_act = p->h_out;
   float* h_score = p->h_out + S * A;
   int32_t* h_iters = reinterpret_cast<int32_t*>(p->h_out + S * A + S);
-  CUDA_TRY(cudaMemcpyAsync(h_act, p->d_out_action, S * A * 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(h_score, p->d_out_score, S * 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(h_iters, p->d_out_iters, S * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(p->h_out, p->d_out, S * (A + 2) * 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   memcpy(out_action_host, h_act, S * A * 4);
   if (out_score_host) memcpy(out_score_host, h_score, S * 4);
