@@ -5,9 +5,13 @@
 // part of mpc_policy.py:30-37 / safe_cem_mpc.py:82-93), with the per-layer GEMMs on the 5th-gen
 // tensor cores:
 //
-//   * one CTA = one ensemble member x NTILES row tiles of 128 rollouts; the member's whole bf16
-//     weight set (144 KB for 4x128) is staged ONCE in shared memory by the TMA engine
-//     (cp.async.bulk of pre-swizzled UMMA images) and reused for all H steps x (L+1) layers;
+//   * PERSISTENT CTAs, one per SM: a CTA walks work items (one ensemble member x NTILES row tiles of 128
+//     rollouts) c, c + grid, ...; the member's whole bf16 weight set (144 KB for 4x128) is staged in
+//     shared memory by the TMA engine (cp.async.bulk of pre-swizzled UMMA images), reused for all H steps
+//     x (L+1) layers of every item of that member and re-staged only when the member changes. Everything
+//     that does not depend on the previous kernel sits before griddepcontrol.wait (PDL);
+//   * single plans (at most SMs / 2 tiles) run a CLUSTER OF TWO CTAs per tile that splits the head pass
+//     by output columns and exchanges the slices through DSMEM (template parameter PAIR, below);
 //   * activations are the A operand and live in TENSOR MEMORY (TS-mode tcgen05.mma: A from TMEM,
 //     B = weights from shared memory), so an MMA streams only the weight tile from SMEM. The bias
 //     of a layer is one more K = 16 MMA (constant ones tile x [bf16(b), bf16(b - hi)] block); layer 0
