@@ -374,8 +374,13 @@ def main():
         tfw = extras['c5']['bf16_20state']['tflops']
         line['roofline_wide'] = {"kernel": "rollout_tc_wide_kernel", "workload": "configs[4] x 20 states per call",
                                  "bound": "tensor", "achieved": tfw, "peak": peak_tf, "unit": "TFLOP/s",
-                                 "frac": tfw / peak_tf, "traffic": None,
-                                 "note": "plan-level: algorithmic flops of the call / CUDA-event time of the call"}
+                                 "frac": tfw / peak_tf, "traffic": committed_traffic("rollout_tc_wide_kernel@c5_20states"),
+                                 "note": "plan-level: algorithmic flops of the call / CUDA-event time of the call; "
+                                         "470 row tiles = 3.18 waves of 148 SMs (the fourth wave is 18 % full)"}
+        if 'bf16_18state' in extras['c5']:
+            tf18 = extras['c5']['bf16_18state']['tflops']
+            line['roofline_wide']['full_waves'] = {"workload": "configs[4] x 18 states per call (430 row tiles = 2.91 waves)",
+                                                   "achieved": tf18, "frac": tf18 / peak_tf}
     if 'c4' in extras and 'tflops_per_gpu' in extras['c4']:
         # the same kernel at a shape that fills the GPU (BASELINE configs[3], 1024 states per call):
         # whole planning calls, so it includes the small CEM kernels (< 1 % of the time there)
@@ -423,12 +428,15 @@ def bench_plain(synthetic, torch, c, precision, states, flush, K):
 def bench_wide(synthetic, torch, flush, cpu=True):
     """BASELINE configs[4]: the wide 10 x (4 x 400) ensemble, horizon 50 — safety-aware (SafeCemMpc,
     penalty) and safety-unaware (CemMpc, reward-only elites) single-state plans on the streaming tcgen05
-    kernel (bf16), the fp32 kernel beside it, plus 5 and 20 states per call (120 / 480 row tiles) for the
-    kernel's throughput, and one plan of the CPU restatement on the host cores."""
+    kernel (bf16), the fp32 kernel beside it, plus 5, 18 and 20 states per call for the kernel's throughput (one
+    128-row tile per SM and wave: 20 states are 470 tiles = 3.18 waves of 148, i.e. a fourth wave that is 18 % full;
+    18 states are 430 tiles = 2.91 waves, the same kernel without that tail), and one plan of the CPU restatement on
+    the host cores."""
     out = {}
     fpt = None
     for objective, precision, S in (('penalty', 'bf16', 1), ('reward', 'bf16', 1), ('penalty', 'fp32', 1),
-                                    ('penalty', 'bf16', 5), ('penalty', 'bf16', 20), ('reward', 'bf16', 20)):
+                                    ('penalty', 'bf16', 5), ('penalty', 'bf16', 18), ('penalty', 'bf16', 20),
+                                    ('reward', 'bf16', 20)):
         c = synthetic.make_workload('c5', S=S, seed=0)
         pol = synthetic.build_policy(c, objective, precision=precision, seed=31)
         st = torch.from_numpy(synthetic.make_state(c['sensors'], seed=500, n_states=S).reshape(S, -1)).cuda()
@@ -446,8 +454,10 @@ def bench_wide(synthetic, torch, flush, cpu=True):
         fpt = synthetic.flops_per_transition(c['O'], c['A'], c['L'], c['U'])
         trans = c['I'] * c['H'] * c['P'] * c['N'] * S
         tag = "%s_%dstate" % (precision, S) if objective == 'penalty' else "%s_%dstate_reward_only" % (precision, S)
+        tiles = c['E'] * ((c['P'] * c['N'] * S // c['E'] + 127) // 128)
         out[tag] = {"objective": "SafeCemMpc penalty" if objective == 'penalty' else "CemMpc reward-only",
-                    "ms_per_call": ms, "plans_per_s": S * 1e3 / ms, "tflops": trans * fpt / (ms * 1e-3) / 1e12}
+                    "ms_per_call": ms, "plans_per_s": S * 1e3 / ms, "tflops": trans * fpt / (ms * 1e-3) / 1e12,
+                    "row_tiles": tiles, "waves_of_148_sms": round(tiles / 148.0, 2)}
     out["workload"] = "configs[4]: E=10 L=4x400 O=60 A=2 H=50 N=150 P=20 I=5; %d flop per transition" % fpt
     if cpu:
         c = synthetic.make_workload('c5', S=1, seed=0)
