@@ -521,6 +521,28 @@ static void build_tiles(const RowGeom& g, int tile_rows, std::vector<Tile>& tile
   }
 }
 
+// Two tiles per work item, persistent CTAs (one per SM): the items of the last, partly filled round are split into
+// single-tile items when that still fits in one round. A lone tile takes ~0.6 of a pair's time (no ping-pong
+// partner, but nothing to share the SM with either), so the launch ends ~0.4 item earlier — 0.5 % at 82 rounds.
+static void split_tail_items(std::vector<Tile>& tiles, int sms) {
+  const size_t n_items = tiles.size() / 2;
+  if (sms <= 0 || n_items <= (size_t)sms) return;
+  const size_t rounds = (n_items + sms - 1) / sms;
+  const size_t last = n_items - (size_t)sms * (rounds - 1);
+  if (2 * last > (size_t)sms) return;
+  std::vector<Tile> tail(tiles.end() - 2 * last, tiles.end());
+  tiles.resize(tiles.size() - 2 * last);
+  for (size_t i = 0; i < tail.size(); i += 2) {
+    for (int h = 0; h < 2; ++h) {
+      if (tail[i + h].count == 0) continue;
+      Tile empty = tail[i + h];
+      empty.k0 = 0; empty.count = 0;
+      tiles.push_back(tail[i + h]);
+      tiles.push_back(empty);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // NCCL, loaded lazily so that a process that already holds torch's bundled libnccl reuses it
 // ---------------------------------------------------------------------------------------------
@@ -733,6 +755,9 @@ extern "C" int simba_planner_create(simba_model_t* model, const simba_planner_co
     // more tiles than SMs: two tiles per CTA so one tile's MMAs overlap the other's epilogue
     p->tiles_per_cta = 2;
     build_tiles(p->geom, p->tile_rows, p->tiles, 2);
+    int sms_now = 0;
+    cudaDeviceGetAttribute(&sms_now, cudaDevAttrMultiProcessorCount, p->device);
+    if (getenv("SIMBA_B200_NO_TAIL_SPLIT") == nullptr) split_tail_items(p->tiles, sms_now);
   }
   {
     // few tiles (a single plan): two SMs per tile, the head pass split between them (rollout_tc.cu, PAIR)
